@@ -1,0 +1,103 @@
+/*
+ * whitomo_b200.h -- C ABI of the B200-native (sm_100a) reconstruction engine.
+ *
+ * This is the drop-in boundary for the reference's operator layer.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).  The reference
+ * reaches ASTRA's single-threaded CPU algorithms through src/astra_proxy.py; a maintainer binds these
+ * symbols with ctypes instead (whitomo_b200/_capi.py is that binding).
+ *
+ * Conventions
+ *  - plain C types only; all data pointers are caller-owned DEVICE pointers (fp32, C order);
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, performs no
+ *    allocation and no synchronisation (handles own a few KB of per-angle constants, created once);
+ *  - the caller provides scratch (`ws`, `ws_bytes`) sized by wt_workspace_bytes();
+ *  - return 0 on success, a negative WT_ERR_* otherwise; wt_last_error() gives the message
+ *    (thread-local); no C++ exception crosses the boundary;
+ *  - "images" are independent 2D problems sharing one geometry: slices of a stack and/or the K
+ *    element maps of the white-beam model.  Volumes are (nimages, rows, cols), sinograms
+ *    (nimages, nangles, ndet), both dense.
+ */
+#ifndef WHITOMO_B200_H
+#define WHITOMO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_OK 0
+#define WT_ERR_INVALID -1      /* bad argument (null pointer, non-positive size, misaligned pointer) */
+#define WT_ERR_UNSUPPORTED -2  /* geometry the kernels do not implement (det_width < 1, non-parallel) */
+#define WT_ERR_WORKSPACE -3    /* ws_bytes smaller than wt_workspace_bytes() */
+#define WT_ERR_CUDA -4         /* a CUDA runtime call failed; message in wt_last_error() */
+
+typedef struct wt_geom wt_geom;         /* parallel-beam geometry + per-angle device constants */
+typedef struct wt_spectrum wt_spectrum; /* polychromatic source / absorption tables on the device */
+
+const char *wt_last_error(void);
+int wt_version(void);
+
+/* Replaces astra.create_proj_geom('parallel', det_width, ndet, angles) + astra.create_vol_geom(rows, cols)
+ * + astra.create_projector('linear', pg, vg)  (src/white_projection.py:41-63, src/white_rec.py:66-74,
+ * teeth_recon/experiments.py:228-235).  `angles` is a HOST array (radians, cast to float32 like ASTRA). */
+int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles,
+                   wt_geom **out);
+void wt_geom_destroy(wt_geom *g);
+int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles);
+
+/* bytes of scratch any call below needs for `nimages` images */
+size_t wt_workspace_bytes(const wt_geom *g, int nimages);
+
+/* p = W x.  Replaces gpu_fp (src/astra_proxy.py:35-49: ASTRA 'FP' with the 'linear' projector).
+ * vol (nimages, rows, cols) -> sino (nimages, nangles, ndet). */
+int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws, size_t ws_bytes,
+          void *stream);
+
+/* g = W^T q (exact transpose).  Replaces gpu_bp (src/astra_proxy.py:52-66: ASTRA 'BP').
+ * sino (nimages, nangles, ndet) -> vol (nimages, rows, cols).  Only angles [angle_begin, angle_end)
+ * contribute (the angle-range split of one oversized slice); pass 0, nangles for the full operator. */
+int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end,
+          void *ws, size_t ws_bytes, void *stream);
+
+/* x = SIRT(p, n_iters), x0 = 0.  Replaces cpu_sirt (src/astra_proxy.py:69-84: ASTRA 'SIRT').
+ * sino (nimages, nangles, ndet) -> vol (nimages, rows, cols). */
+int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_iters, void *ws,
+            size_t ws_bytes, void *stream);
+size_t wt_sirt_workspace_bytes(const wt_geom *g, int nimages);
+
+/* Polychromatic tables.  Replaces the constructor state of WhiteProjection
+ * (src/white_projection.py:23-73): source[E] (already normalised by its integral), bin widths w[E]
+ * (= energy_grid[:,1]), element_absorptions[K][E], pixel_size.  HOST arrays, float64. */
+int wt_spectrum_create(int n_elements, int n_bins, const double *source, const double *widths,
+                       const double *absorptions, double pixel_size, wt_spectrum **out);
+void wt_spectrum_destroy(wt_spectrum *s);
+
+/* White-beam forward model + residual, fused into the projector epilogue.
+ * Replaces FP_white + calc_mu + the residual of func/grad
+ * (src/white_projection.py:86-98,116-127,130-139; src/white_rec.py:111-148):
+ *   P_k = W c_k;  I[r] = sum_e s_e w_e exp(-pix sum_k ea[k,e] P_k[r]);  q = meas - I;
+ *   mu_k[r] = -pix sum_e s_e w_e ea[k,e] exp(...);  qmu_k = q * mu_k;  loss = 1/2 sum_r q^2.
+ * conc (nslices, K, rows, cols); meas (nslices, nangles, ndet) or NULL (then q = -I);
+ * outputs, each optional (NULL to skip): intensity (nslices, nangles, ndet), qmu (nslices, K, nangles, ndet),
+ * loss (nslices) as float64. */
+int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const float *meas,
+                float *intensity, float *qmu, double *loss, int nslices, void *ws, size_t ws_bytes,
+                void *stream);
+
+/* Fused box-barrier gradient step (one inner iteration of barrier_method with the gogo constraints):
+ *   grad = g + beta_reg*reg_w*d|c0 c1|/dc + beta_reg*t*(-1/x + 1/(1-x));  x <- clip(x - alpha*grad, 0, 1)
+ * Replaces src/barrier_method.py:164-206 with the (f,g,proj) tuples of src/barrier_method_gogo.py:79-94
+ * and calc_uneq_reg_grad (src/white_rec.py:180-186).  x, g: (nslices, K, rows, cols); x updated in place.
+ * reg_w = 0 disables the |c0 c1| regulariser (requires K == 2 otherwise); lower_only != 0 keeps only the
+ * x >= 0 barrier and clips to [0, +inf) (the mono MAR 'morezero' constraint, teeth_recon/experiments.py:704-706).
+ * penalty (nslices, float64, optional): sum beta_reg*reg(x') + beta_reg*t*phi(x') at the NEW x, the terms
+ * barrier_method adds to the loss for its early-stop test (src/barrier_method.py:208-213). */
+int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, float alpha,
+                      float beta_reg, float t, float reg_w, int lower_only, double *penalty, void *ws,
+                      size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

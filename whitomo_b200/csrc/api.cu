@@ -1,0 +1,419 @@
+// C ABI of the whitomo_b200 engine (see include/whitomo_b200.h for the contract and the reference
+// interfaces each entry point replaces).  Host side only: argument checks, workspace carving, launches.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "bp.cuh"
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "fp.cuh"
+
+namespace wt {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return WT_ERR_CUDA;
+}
+static int invalid(const char *msg) {
+    g_err = msg;
+    return WT_ERR_INVALID;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carve the caller's scratch into 256-byte aligned pieces
+struct Carver {
+    char *base;
+    size_t off, cap;
+    Carver(void *p, size_t bytes) : base((char *)p), off(0), cap(bytes) {}
+    template <class T> T *take(size_t count) {
+        T *r = (T *)(base + off);
+        off = align_up(off + count * sizeof(T), 256);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+static size_t packed_vol_floats(const wt_geom *g, int n) {
+    return align_up((size_t)n * g->rows * (g->cols + 2 * VPAD), 64) + align_up((size_t)n * g->cols * (g->rows + 2 * VPAD), 64);
+}
+static size_t packed_sino_floats(const wt_geom *g, int n) { return align_up((size_t)n * g->nangles * g->sino_pitch, 64); }
+static int fp_blocks(const wt_geom *g) { return ((g->ndet + FP_DT - 1) / FP_DT) * ((g->nangles + FP_AT - 1) / FP_AT); }
+
+// images are processed in chunks of V in {4,2,1} interleaved images
+struct Chunk { int v, first, groups; };
+static std::vector<Chunk> chunks(int n, int multiple_of = 1) {
+    std::vector<Chunk> c;
+    int first = 0;
+    for (int v = 4; v >= 1; v >>= 1) {
+        if (v % multiple_of) continue;
+        const int gcount = (n - first) / v;
+        if (gcount > 0) { c.push_back({v, first, gcount}); first += gcount * v; }
+    }
+    return c;
+}
+
+template <int V, class Epi>
+static void fp_chunk(const FpParams &p, const Epi &epi, const float *src, float *vn, float *vt, int groups, cudaStream_t st) {
+    if constexpr (V % Epi::kMult == 0) {
+        launch_pack_vol<V>(src, vn, vt, p.R, p.C, groups, st);
+        launch_fp<V>(p, epi, groups, st);
+    }
+}
+
+template <class Epi>
+static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_end, float *vn, float *vt,
+                  const Epi &epi_proto, cudaStream_t st, int multiple_of = 1) {
+    const size_t img = (size_t)g->rows * g->cols;
+    for (const Chunk &c : chunks(n, multiple_of)) {
+        FpParams p;
+        p.vn = vn; p.vt = vt; p.ang = g->d_fp;
+        p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
+        p.a_begin = a_begin; p.a_end = a_end;
+        const float *src = vol + (size_t)c.first * img;
+        Epi epi = epi_proto.offset(c.first);
+        switch (c.v) {
+        case 4: fp_chunk<4>(p, epi, src, vn, vt, c.groups, st); break;
+        case 2: fp_chunk<2>(p, epi, src, vn, vt, c.groups, st); break;
+        default: fp_chunk<1>(p, epi, src, vn, vt, c.groups, st); break;
+        }
+        WT_CUDA(cudaGetLastError());
+    }
+    return WT_OK;
+}
+
+template <class Epi>
+static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
+                  cudaStream_t st) {
+    const size_t plane = (size_t)g->nangles * g->ndet;
+    for (const Chunk &c : chunks(n)) {
+        BpParams p;
+        p.sp = sp; p.ang = g->d_bp;
+        p.R = g->rows; p.C = g->cols; p.A = g->nangles;
+        p.padl = g->sino_padl; p.pitch = g->sino_pitch;
+        p.a_begin = a_begin; p.a_end = a_end;
+        const float *src = sino + (size_t)c.first * plane;
+        Epi epi = epi_proto.offset(c.first);
+        switch (c.v) {
+        case 4: launch_pack_sino<4>(src, sp, g, c.groups, st); WT_CUDA(launch_bp<4>(p, epi, c.groups, st)); break;
+        case 2: launch_pack_sino<2>(src, sp, g, c.groups, st); WT_CUDA(launch_bp<2>(p, epi, c.groups, st)); break;
+        default: launch_pack_sino<1>(src, sp, g, c.groups, st); WT_CUDA(launch_bp<1>(p, epi, c.groups, st)); break;
+        }
+        WT_CUDA(cudaGetLastError());
+    }
+    return WT_OK;
+}
+
+// host-side wrappers that know how to shift their pointers to the first image of a chunk
+struct HFpStore : FpEpiStore {
+    static constexpr int kMult = 1;
+    size_t plane;
+    HFpStore offset(int first) const { HFpStore e = *this; e.sino = sino + (size_t)first * plane; return e; }
+};
+struct HFpSirt : FpEpiSirtResidual {
+    static constexpr int kMult = 1;
+    size_t plane;
+    HFpSirt offset(int first) const {
+        HFpSirt e = *this; e.meas = meas + (size_t)first * plane; e.out = out + (size_t)first * plane; return e;
+    }
+};
+struct HBpStore : BpEpiStore {
+    size_t img;
+    HBpStore offset(int first) const { HBpStore e = *this; e.vol = vol + (size_t)first * img; return e; }
+};
+struct HBpSirt : BpEpiSirtUpdate {
+    size_t img;
+    HBpSirt offset(int first) const { HBpSirt e = *this; e.vol = vol + (size_t)first * img; return e; }
+};
+template <int K>
+struct HFpWhite : FpEpiWhite<K> {
+    static constexpr int kMult = K;
+    size_t plane;
+    int nblocks;
+    HFpWhite offset(int first) const {
+        HFpWhite e = *this;
+        const size_t s0 = (size_t)first / K;
+        if (e.meas) e.meas += s0 * plane;
+        if (e.inten) e.inten += s0 * plane;
+        if (e.qmu) e.qmu += (size_t)first * plane;
+        if (e.partial) e.partial += s0 * nblocks;
+        return e;
+    }
+};
+
+}  // namespace wt
+
+using namespace wt;
+
+extern "C" {
+
+const char *wt_last_error(void) { return g_err.c_str(); }
+int wt_version(void) { return 100; }
+
+int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, wt_geom **out) {
+    if (!out || !angles) return invalid("wt_geom_create: null pointer");
+    if (rows <= 0 || cols <= 0 || ndet <= 0 || nangles <= 0) return invalid("wt_geom_create: sizes must be positive");
+    if (!(det_width >= 1.0f)) {
+        g_err = "wt_geom_create: det_width < 1 needs more than two backprojection taps (unsupported)";
+        return WT_ERR_UNSUPPORTED;
+    }
+    std::vector<FpAngle> fp(nangles);
+    std::vector<BpAngle> bp(nangles);
+    const double Ex = -0.5 * cols + 0.5, Ey = 0.5 * rows - 0.5;
+    for (int a = 0; a < nangles; ++a) {
+        // the float32 fields ASTRA's vector geometry would hold for this angle
+        const double th = (double)angles[a];
+        const double cs = cos(th), sn = sin(th);
+        const float ray_x = (float)(-sn), ray_y = (float)cs;
+        const float ux = (float)((double)det_width * cs), uy = (float)((double)det_width * sn);
+        const float sx = (float)((double)det_width * -0.5 * (double)ndet * cs);
+        const float sy = (float)((double)det_width * -0.5 * (double)ndet * sn);
+        const int vertical = fabsf(ray_x) < fabsf(ray_y);
+        FpAngle &f = fp[a];
+        f.vertical = vertical;
+        f.pad_ = 0;
+        float ratio;
+        if (vertical) {
+            ratio = ray_x / ray_y;
+            f.len = sqrtf(ray_y * ray_y + ray_x * ray_x) / fabsf(ray_y);
+            // c = Dx + (Ey - Dy) * ratio - Ex,  Dx = sx + (d + .5) ux,  Dy = sy + (d + .5) uy
+            f.c0_base = (double)sx + (Ey - (double)sy) * (double)ratio - Ex;
+            f.c0_step = (double)ux - (double)uy * (double)ratio;
+        } else {
+            ratio = ray_y / ray_x;
+            f.len = sqrtf(ray_y * ray_y + ray_x * ray_x) / fabsf(ray_x);
+            // r = -(Dy + (Ex - Dx) * ratio - Ey)
+            f.c0_base = -((double)sy + (Ex - (double)sx) * (double)ratio - Ey);
+            f.c0_step = -((double)uy - (double)ux * (double)ratio);
+        }
+        f.delta = -ratio;
+        // gather form: pixel (line l, position k) sits at detector coordinate d* = (k - c0_base - l*delta)/c0_step - 0.5
+        BpAngle &b = bp[a];
+        const double inv = 1.0 / f.c0_step;
+        const double dk = inv, dl = -(double)f.delta * inv;
+        b.d00 = -f.c0_base * inv - 0.5;
+        b.dcol = vertical ? dk : dl;
+        b.drow = vertical ? dl : dk;
+        b.a0 = f.len;
+        b.b = (float)((double)f.len * fabs(f.c0_step));
+        b.a1 = (float)((double)f.len - (double)f.len * fabs(f.c0_step));
+        b.pad_ = 0.0f;
+    }
+    wt_geom *g = new wt_geom();
+    g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
+    // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row
+    const double halfdiag = 0.5 * sqrt((double)rows * rows + (double)cols * cols) / (double)det_width;
+    int padl = (int)ceil(halfdiag - (0.5 * ndet - 0.5)) + 3;
+    if (padl < 4) padl = 4;
+    padl = (padl + 3) & ~3;
+    g->sino_padl = padl;
+    g->sino_pitch = (padl + ndet + padl + BP_SEGW + 3) & ~3;
+    g->d_fp = nullptr; g->d_bp = nullptr;
+    g->h_angles = (float *)malloc(sizeof(float) * nangles);
+    memcpy(g->h_angles, angles, sizeof(float) * nangles);
+    cudaError_t e = cudaMalloc(&g->d_fp, sizeof(FpAngle) * nangles);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_bp, sizeof(BpAngle) * nangles);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_fp, fp.data(), sizeof(FpAngle) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_bp, bp.data(), sizeof(BpAngle) * nangles, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        wt_geom_destroy(g);
+        return cuda_fail(e, "wt_geom_create");
+    }
+    *out = g;
+    return WT_OK;
+}
+
+void wt_geom_destroy(wt_geom *g) {
+    if (!g) return;
+    if (g->d_fp) cudaFree(g->d_fp);
+    if (g->d_bp) cudaFree(g->d_bp);
+    free(g->h_angles);
+    delete g;
+}
+
+int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles) {
+    if (!g) return invalid("wt_geom_dims: null geometry");
+    if (rows) *rows = g->rows;
+    if (cols) *cols = g->cols;
+    if (ndet) *ndet = g->ndet;
+    if (nangles) *nangles = g->nangles;
+    return WT_OK;
+}
+
+size_t wt_workspace_bytes(const wt_geom *g, int nimages) {
+    if (!g || nimages <= 0) return 0;
+    size_t fl = packed_vol_floats(g, nimages) + packed_sino_floats(g, nimages);
+    fl += align_up((size_t)nimages * fp_blocks(g), 64);                      // loss partials (float)
+    size_t bytes = fl * sizeof(float) + align_up((size_t)nimages * UPD_BLOCKS_PER_SLICE * sizeof(double), 256);
+    return bytes + 4096;
+}
+
+int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws, size_t ws_bytes, void *stream) {
+    if (!g || !vol || !sino || !ws) return invalid("wt_fp: null pointer");
+    if (nimages <= 0) return invalid("wt_fp: nimages must be positive");
+    if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_fp: workspace too small"; return WT_ERR_WORKSPACE; }
+    Carver cv(ws, ws_bytes);
+    float *vn = cv.take<float>((size_t)nimages * g->rows * (g->cols + 2 * VPAD));
+    float *vt = cv.take<float>((size_t)nimages * g->cols * (g->rows + 2 * VPAD));
+    HFpStore epi;
+    epi.sino = sino;
+    epi.plane = (size_t)g->nangles * g->ndet;
+    return run_fp(g, vol, nimages, 0, g->nangles, vn, vt, epi, (cudaStream_t)stream);
+}
+
+int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, void *ws,
+          size_t ws_bytes, void *stream) {
+    if (!g || !vol || !sino || !ws) return invalid("wt_bp: null pointer");
+    if (nimages <= 0) return invalid("wt_bp: nimages must be positive");
+    if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_bp: bad angle range");
+    if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_bp: workspace too small"; return WT_ERR_WORKSPACE; }
+    Carver cv(ws, ws_bytes);
+    float *sp = cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
+    HBpStore epi;
+    epi.vol = vol;
+    epi.scale = 1.0f;
+    epi.img = (size_t)g->rows * g->cols;
+    return run_bp(g, sino, nimages, angle_begin, angle_end, sp, epi, (cudaStream_t)stream);
+}
+
+size_t wt_sirt_workspace_bytes(const wt_geom *g, int nimages) {
+    if (!g || nimages <= 0) return 0;
+    const size_t plane = (size_t)g->nangles * g->ndet, img = (size_t)g->rows * g->cols;
+    return wt_workspace_bytes(g, nimages) + (align_up(plane, 64) + align_up(img, 64) + align_up((size_t)nimages * plane, 64)) * sizeof(float) + 1024;
+}
+
+int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_iters, void *ws, size_t ws_bytes,
+            void *stream) {
+    if (!g || !vol || !sino || !ws) return invalid("wt_sirt: null pointer");
+    if (nimages <= 0 || n_iters < 0) return invalid("wt_sirt: bad counts");
+    if (ws_bytes < wt_sirt_workspace_bytes(g, nimages)) { g_err = "wt_sirt: workspace too small"; return WT_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)g->nangles * g->ndet, img = (size_t)g->rows * g->cols;
+    Carver cv(ws, ws_bytes);
+    float *vn = cv.take<float>((size_t)nimages * g->rows * (g->cols + 2 * VPAD));
+    float *vt = cv.take<float>((size_t)nimages * g->cols * (g->rows + 2 * VPAD));
+    float *sp = cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
+    float *raysum = cv.take<float>(plane);
+    float *pixsum = cv.take<float>(img);
+    float *resid = cv.take<float>((size_t)nimages * plane);
+    // Rsum = W 1, Csum = W^T 1 (the residual buffer doubles as the all-ones input)
+    fill_kernel<<<296, 256, 0, st>>>(vol, img, 1.0f);
+    HFpStore fs; fs.sino = raysum; fs.plane = plane;
+    int rc = run_fp(g, vol, 1, 0, g->nangles, vn, vt, fs, st);
+    if (rc) return rc;
+    fill_kernel<<<296, 256, 0, st>>>(resid, plane, 1.0f);
+    HBpStore bs; bs.vol = pixsum; bs.scale = 1.0f; bs.img = img;
+    rc = run_bp(g, resid, 1, 0, g->nangles, sp, bs, st);
+    if (rc) return rc;
+    WT_CUDA(cudaMemsetAsync(vol, 0, sizeof(float) * nimages * img, st));
+    for (int it = 0; it < n_iters; ++it) {
+        HFpSirt fe; fe.meas = sino; fe.raysum = raysum; fe.out = resid; fe.plane = plane;
+        rc = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, fe, st);
+        if (rc) return rc;
+        HBpSirt be; be.vol = vol; be.pixsum = pixsum; be.img = img;
+        rc = run_bp(g, resid, nimages, 0, g->nangles, sp, be, st);
+        if (rc) return rc;
+    }
+    return WT_OK;
+}
+
+int wt_spectrum_create(int n_elements, int n_bins, const double *source, const double *widths, const double *absorptions,
+                       double pixel_size, wt_spectrum **out) {
+    if (!out || !source || !widths || !absorptions) return invalid("wt_spectrum_create: null pointer");
+    if (n_elements <= 0 || n_bins <= 0) return invalid("wt_spectrum_create: sizes must be positive");
+    std::vector<float> tab((size_t)(n_elements + 1) * n_bins);
+    for (int e = 0; e < n_bins; ++e) tab[e] = (float)(source[e] * widths[e]);
+    for (int k = 0; k < n_elements; ++k)
+        for (int e = 0; e < n_bins; ++e) tab[(size_t)(k + 1) * n_bins + e] = (float)(pixel_size * absorptions[(size_t)k * n_bins + e]);
+    wt_spectrum *s = new wt_spectrum();
+    s->K = n_elements; s->E = n_bins; s->d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&s->d_tab, tab.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { wt_spectrum_destroy(s); return cuda_fail(e, "wt_spectrum_create"); }
+    *out = s;
+    return WT_OK;
+}
+
+void wt_spectrum_destroy(wt_spectrum *s) {
+    if (!s) return;
+    if (s->d_tab) cudaFree(s->d_tab);
+    delete s;
+}
+
+int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const float *meas, float *intensity,
+                float *qmu, double *loss, int nslices, void *ws, size_t ws_bytes, void *stream) {
+    if (!g || !s || !conc || !ws) return invalid("wt_white_fp: null pointer");
+    if (nslices <= 0) return invalid("wt_white_fp: nslices must be positive");
+    const int K = s->K, n = nslices * K;
+    if (ws_bytes < wt_workspace_bytes(g, n)) { g_err = "wt_white_fp: workspace too small"; return WT_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)g->nangles * g->ndet;
+    Carver cv(ws, ws_bytes);
+    float *vn = cv.take<float>((size_t)n * g->rows * (g->cols + 2 * VPAD));
+    float *vt = cv.take<float>((size_t)n * g->cols * (g->rows + 2 * VPAD));
+    float *sp = cv.take<float>((size_t)n * g->nangles * g->sino_pitch);  // generic-K path: holds P (n, A, D)
+    float *partial = cv.take<float>((size_t)n * fp_blocks(g));
+    int nb = 0;
+    if (K == 1 || K == 2) {
+        nb = fp_blocks(g);
+        int rc;
+        if (K == 1) {
+            HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
+            e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
+            rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, e, st, 1);
+        } else {
+            HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
+            e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
+            rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, e, st, 2);
+        }
+        if (rc) return rc;
+    } else {
+        HFpStore fs; fs.sino = sp; fs.plane = plane;
+        int rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, fs, st);
+        if (rc) return rc;
+        nb = (int)((plane + 255) / 256);
+        white_epilogue_kernel<<<dim3(nb, nslices), 256, 0, st>>>(sp, s->d_tab, K, s->E, meas, intensity, qmu,
+                                                                  loss ? partial : nullptr, plane);
+        WT_CUDA(cudaGetLastError());
+    }
+    if (loss) {
+        reduce_partials_kernel<<<nslices, 32, 0, st>>>(partial, nb, 0.5, loss);
+        WT_CUDA(cudaGetLastError());
+    }
+    return WT_OK;
+}
+
+int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, float alpha, float beta_reg,
+                      float t, float reg_w, int lower_only, double *penalty, void *ws, size_t ws_bytes, void *stream) {
+    if (!x || !grad) return invalid("wt_barrier_update: null pointer");
+    if (nslices <= 0 || n_elements <= 0 || n_elements > 4 || npix == 0) return invalid("wt_barrier_update: bad sizes (1 <= K <= 4)");
+    if (reg_w != 0.0f && n_elements != 2) return invalid("wt_barrier_update: the |c0 c1| regulariser needs K == 2");
+    double *partial = nullptr;
+    if (penalty) {
+        if (!ws || ws_bytes < (size_t)nslices * UPD_BLOCKS_PER_SLICE * sizeof(double)) { g_err = "wt_barrier_update: workspace too small"; return WT_ERR_WORKSPACE; }
+        partial = (double *)ws;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int bx = (int)((npix + 255) / 256);
+    if (bx > UPD_BLOCKS_PER_SLICE) bx = UPD_BLOCKS_PER_SLICE;
+    dim3 grid(bx, nslices);
+    switch (n_elements) {
+    case 1: barrier_update_kernel<1><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
+    case 2: barrier_update_kernel<2><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
+    case 3: barrier_update_kernel<3><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
+    default: barrier_update_kernel<4><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
+    }
+    WT_CUDA(cudaGetLastError());
+    if (penalty) {
+        reduce_partials_f64_kernel<<<nslices, 32, 0, st>>>(partial, bx, 1.0, penalty);
+        WT_CUDA(cudaGetLastError());
+    }
+    return WT_OK;
+}
+
+}  // extern "C"

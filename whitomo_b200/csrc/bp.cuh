@@ -1,0 +1,190 @@
+// K2: pixel-driven backprojector, the exact transpose of K1 in gather form:
+//   v[row, col] = sum_a  w0 * q[a, d0] + w1 * q[a, d0 + 1],   d0 = floor(d*),  f = d* - d0,
+//   w0 = max(0, A0 - B f),  w1 = max(0, A1 + B f)           (triangle of half-width m, height 1/m).
+//
+// A CTA owns a BP_TW x BP_TH pixel tile and keeps 8 pixels x V images per thread in registers.  For
+// every block of BP_AB angles one warp computes, per angle, where the tile's shadow falls on the
+// detector and asks the TMA unit (cp.async.bulk, one 1-D bulk copy per angle) to stage that
+// BP_SEGW-wide sinogram segment in shared memory; completion is tracked with an mbarrier per stage,
+// BP_STAGES stages deep, so the copies of later angle blocks overlap the gather of the current one.
+// Lanes run along image columns: their detector positions differ by |cos| <= 1, so the LDS of a warp
+// touches at most 32 consecutive words -- conflict-free.
+#pragma once
+#include "common.cuh"
+
+namespace wt {
+
+// ---- packing: plain (n, A, D) -> SP (G, A, pitch, V) with `padl` zero detectors in front ------------
+template <int V>
+__global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict__ sino, float *__restrict__ sp, int A,
+                                                        int D, int padl, int pitch) {
+    typedef typename VecOf<V>::T VecT;
+    const int g = blockIdx.z, a = blockIdx.y;
+    const size_t plane = (size_t)A * D;
+    for (int dp = blockIdx.x * blockDim.x + threadIdx.x; dp < pitch; dp += gridDim.x * blockDim.x) {
+        const int d = dp - padl;
+        float v[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            v[i] = (d >= 0 && d < D) ? __ldg(sino + ((size_t)g * V + i) * plane + (size_t)a * D + d) : 0.0f;
+        reinterpret_cast<VecT *>(sp)[((size_t)g * A + a) * pitch + dp] = pack<V>(v);
+    }
+}
+
+template <int V>
+inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, cudaStream_t st) {
+    dim3 grid((g->sino_pitch + 255) / 256, g->nangles, groups);
+    pack_sino_kernel<V><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch);
+}
+
+struct BpParams {
+    const float *sp;  // packed sinogram (G, A, pitch, V)
+    const BpAngle *ang;
+    int R, C, A;
+    int padl, pitch;
+    int a_begin, a_end;
+};
+
+// plain store: vol (n, R, C)
+struct BpEpiStore {
+    float *vol;
+    float scale;
+    template <int V>
+    __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col,
+                                               const float (&val)[V]) const {
+        const size_t img = (size_t)p.R * p.C;
+#pragma unroll
+        for (int i = 0; i < V; ++i) vol[((size_t)g * V + i) * img + (size_t)row * p.C + col] = scale * val[i];
+    }
+};
+
+template <int V>
+struct BpSmem {
+    typedef typename VecOf<V>::T VecT;
+    VecT seg[BP_STAGES][BP_AB][BP_SEGW];
+    float4 cst[BP_STAGES][BP_AB];  // dcol, drow, base, a0
+    float2 cst2[BP_STAGES][BP_AB]; // a1, b
+    uint64_t full[BP_STAGES];
+};
+
+template <int V, class Epi>
+__global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
+    typedef typename VecOf<V>::T VecT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BpSmem<V> &sm = *reinterpret_cast<BpSmem<V> *>(smem_raw);
+
+    const int g = blockIdx.z;
+    const int col0 = blockIdx.x * BP_TW, row0 = blockIdx.y * BP_TH;
+    const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.R - row0);  // real pixels of this tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nblk = (p.a_end - p.a_begin + BP_AB - 1) / BP_AB;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < BP_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer (warp 0): stage angle block `blk`
+    auto produce = [&](int blk) {
+        const int s = blk % BP_STAGES;
+        const int a = p.a_begin + blk * BP_AB + lane;
+        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        const VecT *src = nullptr;
+        if (lane < nvalid) {
+            const BpAngle an = p.ang[a];
+            const double d_t00 = an.d00 + (double)col0 * an.dcol + (double)row0 * an.drow;
+            const double dmin = d_t00 + fmin(0.0, (double)(tw - 1) * an.dcol) + fmin(0.0, (double)(th - 1) * an.drow);
+            const int lo = (int)floor(dmin) - 1 + p.padl;  // >= 0 by construction of padl
+            const int aligned = lo & ~3;
+            sm.cst[s][lane] = make_float4((float)an.dcol, (float)an.drow, (float)(d_t00 + (double)(p.padl - aligned)), an.a0);
+            sm.cst2[s][lane] = make_float2(an.a1, an.b);
+            src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
+        __syncwarp();
+        if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
+    };
+
+    if (warp == 0) {
+        for (int b = 0; b < BP_STAGES - 1 && b < nblk; ++b) produce(b);
+    }
+
+    // this thread's pixels: columns lane, lane+32; rows warp, warp+8, warp+16, warp+24 (clamped into the
+    // real tile so that every smem index stays inside the staged segment; clamped results are dropped)
+    float jc[2], ir[4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) jc[c] = (float)min(lane + 32 * c, tw - 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ir[r] = (float)min(warp + 8 * r, th - 1);
+
+    float acc[4][2][V];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[r][c][i] = 0.0f;
+
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int s = blk % BP_STAGES;
+        if (warp == 0 && blk + BP_STAGES - 1 < nblk) {
+            fence_proxy_async();
+            produce(blk + BP_STAGES - 1);
+        }
+        mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
+        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        for (int k = 0; k < nvalid; ++k) {
+            const float4 c4 = sm.cst[s][k];
+            const float2 c2 = sm.cst2[s][k];
+            const VecT *seg = &sm.seg[s][k][0];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float dr = fmaf(ir[r], c4.y, c4.z);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float ds = fmaf(jc[c], c4.x, dr);
+                    const float fl = floorf(ds);
+                    const float f = ds - fl;
+                    const int idx = (int)fl;
+                    const float w0 = fmaxf(0.0f, fmaf(-c2.y, f, c4.w));
+                    const float w1 = fmaxf(0.0f, fmaf(c2.y, f, c2.x));
+                    float v0[V], v1[V];
+                    unpack<V>(seg[idx], v0);
+                    unpack<V>(seg[idx + 1], v1);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) acc[r][c][i] = fmaf(w0, v0[i], fmaf(w1, v1[i], acc[r][c][i]));
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with stage s before it is refilled
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = row0 + warp + 8 * r;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = col0 + lane + 32 * c;
+            if (row < p.R && col < p.C) epi.template operator()<V>(p, g, row, col, acc[r][c]);
+        }
+    }
+}
+
+template <int V, class Epi>
+inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
+    const size_t smem = sizeof(BpSmem<V>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.R + BP_TH - 1) / BP_TH, groups);
+    bp_kernel<V, Epi><<<grid, BP_THREADS, smem, st>>>(p, epi);
+    return cudaSuccess;
+}
+
+}  // namespace wt

@@ -1,0 +1,149 @@
+// Shared device helpers and the geometry handle of the whitomo_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/whitomo_b200.h"
+
+namespace wt {
+
+// ---- layout constants -------------------------------------------------------------------------
+// Packed volumes carry VPAD zero positions on both sides of every line so that the two Joseph taps of
+// any in-range (and up to 3 positions out-of-range) ray position are always readable: no bounds
+// predicates in the projector's inner loop.
+constexpr int VPAD = 4;
+
+// Backprojector tile: BP_TW x BP_TH pixels per CTA, BP_AB angles per TMA stage, BP_STAGES stages.
+constexpr int BP_TW = 64;
+constexpr int BP_TH = 32;
+constexpr int BP_AB = 16;
+constexpr int BP_STAGES = 3;
+constexpr int BP_SEGW = 80;  // floats per staged sinogram segment (>= tile extent + 7, multiple of 4)
+constexpr int BP_THREADS = 256;
+
+// ---- per-angle constants ------------------------------------------------------------------------
+// FP: position along the interpolation axis for line l and detector d is
+//     c(l, d) = c0_base + (d + 0.5) * c0_step + l * delta        (ASTRA linear projector)
+// with the float32 vector-geometry fields ASTRA would hold, combined in double once per ray.
+struct FpAngle {
+    double c0_base;
+    double c0_step;
+    float delta;    // tan(theta) (vertical) or cot(theta) (horizontal), float32 like the reference
+    float len;      // 1/|cos| or 1/|sin|
+    int vertical;   // |ray_x| < |ray_y| evaluated on float32 values
+    int pad_;
+};
+
+// BP (gather form of the exact transpose, SURVEY A.3, derived from the same FpAngle so that
+// BP == FP^T including the float32 rounding of the constants):
+//     d*(row, col) = d00 + col * dcol + row * drow;  taps floor(d*), floor(d*)+1 with weights
+//     max(0, A0 - B f) and max(0, A1 + B f),  f = frac(d*),  A0 = len, B = len*|c0_step|, A1 = A0 - B.
+struct BpAngle {
+    double d00;
+    double dcol;
+    double drow;
+    float a0, a1, b;
+    float pad_;
+};
+
+}  // namespace wt
+
+struct wt_geom {
+    int rows, cols, ndet, nangles;
+    float det_width;
+    int sino_padl;   // zero detectors in front of every packed sinogram row
+    int sino_pitch;  // packed sinogram row pitch in detector positions (multiple of 4)
+    wt::FpAngle *d_fp;
+    wt::BpAngle *d_bp;
+    float *h_angles;
+};
+
+struct wt_spectrum {
+    int K, E;
+    float *d_tab;  // [E] s_e*w_e, then K rows [E] of pix*ea[k,e]
+};
+
+namespace wt {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define WT_CUDA(call)                                                 \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return wt::cuda_fail(e__, #call);     \
+    } while (0)
+
+// ---- small vector helpers (V images interleaved per position) -----------------------------------
+template <int V> struct VecOf;
+template <> struct VecOf<1> { typedef float T; };
+template <> struct VecOf<2> { typedef float2 T; };
+template <> struct VecOf<4> { typedef float4 T; };
+
+template <int V> __device__ __forceinline__ void unpack(const typename VecOf<V>::T &t, float (&v)[V]);
+template <> __device__ __forceinline__ void unpack<1>(const float &t, float (&v)[1]) { v[0] = t; }
+template <> __device__ __forceinline__ void unpack<2>(const float2 &t, float (&v)[2]) { v[0] = t.x; v[1] = t.y; }
+template <> __device__ __forceinline__ void unpack<4>(const float4 &t, float (&v)[4]) {
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+template <int V> __device__ __forceinline__ typename VecOf<V>::T pack(const float (&v)[V]);
+template <> __device__ __forceinline__ float pack<1>(const float (&v)[1]) { return v[0]; }
+template <> __device__ __forceinline__ float2 pack<2>(const float (&v)[2]) { return make_float2(v[0], v[1]); }
+template <> __device__ __forceinline__ float4 pack<4>(const float (&v)[4]) {
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + TMA (1D bulk copy) ----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WT_DONE_%=;\n"
+        "bra WT_WAIT_%=;\n"
+        "WT_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` in bytes.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace wt

@@ -1,0 +1,228 @@
+// Fused epilogues of K1/K2 and the streaming kernels around them (K3 and small reductions).
+#pragma once
+#include "bp.cuh"
+#include "common.cuh"
+#include "fp.cuh"
+
+namespace wt {
+
+// ---- SIRT (ASTRA CSirtAlgorithm): d = (p - W x) / Rsum, x += (W^T d) / Csum, guarded -----
+struct FpEpiSirtResidual {
+    const float *meas;    // (n, A, D)
+    const float *raysum;  // (A, D)
+    float *out;           // (n, A, D)
+    template <int V>
+    __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
+                                               const float (&val)[V]) const {
+        if (!valid) return;
+        const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
+        const float rs = __ldg(raysum + r);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const size_t o = ((size_t)g * V + i) * plane + r;
+            const float diff = __ldg(meas + o) - val[i];
+            out[o] = rs > 0.000001f ? diff / rs : 0.0f;
+        }
+    }
+};
+
+struct BpEpiSirtUpdate {
+    float *vol;           // (n, R, C), updated in place
+    const float *pixsum;  // (R, C)
+    template <int V>
+    __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col,
+                                               const float (&val)[V]) const {
+        const size_t img = (size_t)p.R * p.C, px = (size_t)row * p.C + col;
+        const float cs = __ldg(pixsum + px);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const size_t o = ((size_t)g * V + i) * img + px;
+            vol[o] += cs > 0.000001f ? val[i] / cs : 0.0f;
+        }
+    }
+};
+
+__global__ void fill_kernel(float *p, size_t n, float v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- white-beam model fused into the projector (src/white_projection.py:86-98,116-139) -----------------
+// A group of V interleaved images holds V/K slices x K elements (image index = slice*K + k).
+template <int K>
+struct FpEpiWhite {
+    const float *tab;   // [E] s_e*w_e, then K x [E] pix*ea[k][e]
+    int E;
+    const float *meas;  // (S, A, D) or null
+    float *inten;       // (S, A, D) or null
+    float *qmu;         // (S, K, A, D) or null
+    float *partial;     // (S, nblocks) per-CTA sums of q^2, or null
+    template <int V>
+    __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
+                                               const float (&val)[V]) const {
+        static_assert(V % K == 0, "group must hold whole slices");
+        constexpr int SPG = V / K;
+        __shared__ float red[SPG][FP_DT * FP_AT / 32];
+        const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
+        const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int sl = 0; sl < SPG; ++sl) {
+            const size_t slice = (size_t)g * SPG + sl;
+            float q2 = 0.0f;
+            if (valid) {
+                float I = 0.0f, mu[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) mu[k] = 0.0f;
+                for (int e = 0; e < E; ++e) {
+                    float arg = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) arg = fmaf(__ldg(tab + (k + 1) * E + e), val[sl * K + k], arg);
+                    const float t = __ldg(tab + e) * expf(-arg);
+                    I += t;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, __ldg(tab + (k + 1) * E + e), mu[k]);
+                }
+                const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
+                if (inten) inten[slice * plane + r] = I;
+                if (qmu) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-mu[k]);
+                }
+                q2 = q * q;
+            }
+            if (partial) {
+                q2 = warp_sum(q2);
+                if ((tid & 31) == 0) red[sl][tid >> 5] = q2;
+            }
+        }
+        if (partial) {
+            __syncthreads();
+            if (tid < SPG) {
+                float s = 0.0f;
+#pragma unroll
+                for (int w = 0; w < FP_DT * FP_AT / 32; ++w) s += red[tid][w];
+                partial[((size_t)g * SPG + tid) * nblocks + bid] = s;
+            }
+        }
+    }
+};
+
+// generic-K path: P (S, K, A, D) already projected; one thread per ray
+__global__ void white_epilogue_kernel(const float *__restrict__ P, const float *__restrict__ tab, int K, int E,
+                                      const float *__restrict__ meas, float *inten, float *qmu, float *partial,
+                                      size_t plane) {
+    const size_t slice = blockIdx.y;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float q2 = 0.0f;
+    if (r < plane) {
+        float I = 0.0f;
+        for (int e = 0; e < E; ++e) {
+            float arg = 0.0f;
+            for (int k = 0; k < K; ++k) arg = fmaf(__ldg(tab + (k + 1) * E + e), __ldg(P + (slice * K + k) * plane + r), arg);
+            I += __ldg(tab + e) * expf(-arg);
+        }
+        const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
+        if (inten) inten[slice * plane + r] = I;
+        if (qmu) {
+            for (int k = 0; k < K; ++k) {
+                float mu = 0.0f;
+                for (int e = 0; e < E; ++e) {
+                    float arg = 0.0f;
+                    for (int kk = 0; kk < K; ++kk)
+                        arg = fmaf(__ldg(tab + (kk + 1) * E + e), __ldg(P + (slice * K + kk) * plane + r), arg);
+                    mu = fmaf(__ldg(tab + e) * expf(-arg), __ldg(tab + (k + 1) * E + e), mu);
+                }
+                qmu[(slice * K + k) * plane + r] = q * (-mu);
+            }
+        }
+        q2 = q * q;
+    }
+    if (partial) {
+        __shared__ float red[8];
+        q2 = warp_sum(q2);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.0f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+            partial[slice * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// out[s] = scale * sum_b partial[s][b]   (fixed order, float64) -- one warp per slice
+__global__ void reduce_partials_kernel(const float *__restrict__ partial, int nb, double scale, double *out) {
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) acc += (double)partial[(size_t)s * nb + b];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[s] = scale * acc;
+}
+__global__ void reduce_partials_f64_kernel(const double *__restrict__ partial, int nb, double scale, double *out) {
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) acc += partial[(size_t)s * nb + b];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[s] = scale * acc;
+}
+
+// ---- K3: fused box-barrier gradient step (src/barrier_method.py:164-206, gogo constraints) -------------
+// One thread per pixel handles all K elements of one slice (K <= 4).  HBM-bound: reads x, g; writes x.
+constexpr int UPD_BLOCKS_PER_SLICE = 296;  // 2 CTAs per SM worth of partials per slice
+
+template <int K>
+__global__ void __launch_bounds__(256) barrier_update_kernel(float *__restrict__ x, const float *__restrict__ grad,
+                                                             size_t npix, float alpha, float beta, float t, float reg_w,
+                                                             int lower_only, double *partial) {
+    const size_t slice = blockIdx.y;
+    float *xs = x + slice * K * npix;
+    const float *gs = grad + slice * K * npix;
+    double pen = 0.0;
+    const float bt = beta * t;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        float xv[K], xn[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) xv[k] = xs[k * npix + i];
+        float sgn = 0.0f;
+        if (K == 2 && reg_w != 0.0f) {
+            const float pr = xv[0] * xv[1];
+            sgn = pr > 0.0f ? 1.0f : (pr < 0.0f ? -1.0f : 0.0f);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float gt = __ldg(gs + k * npix + i);
+            if (K == 2 && reg_w != 0.0f) gt += beta * (reg_w * (xv[1 - k] * sgn));
+            gt += bt * (-1.0f / xv[k]);
+            if (!lower_only) gt += bt * (1.0f / (1.0f - xv[k]));
+            float v = xv[k] - alpha * gt;
+            v = fmaxf(v, 0.0f);
+            if (!lower_only) v = fminf(v, 1.0f);
+            xn[k] = v;
+            xs[k * npix + i] = v;
+        }
+        if (partial) {
+            float ph = 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                ph += xn[k] > 0.0f ? -logf(xn[k]) : INFINITY;
+                if (!lower_only) ph += xn[k] < 1.0f ? -logf(1.0f - xn[k]) : INFINITY;
+            }
+            float rg = 0.0f;
+            if (K == 2 && reg_w != 0.0f) rg = reg_w * fabsf(xn[0] * xn[1]);
+            pen += (double)(beta * rg + bt * ph);
+        }
+    }
+    if (partial) {
+        __shared__ double red[8];
+        pen = warp_sum(pen);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pen;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            partial[slice * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+}  // namespace wt

@@ -1,0 +1,196 @@
+"""Device-tensor interface to the sm_100a kernels: one ``Projector`` per (volume geometry, projection
+geometry) pair -- the object ``astra.create_projector('linear', pg, vg)`` stands for in the reference
+(src/white_projection.py:61-63).  PyTorch is used for device memory and streams only; all arithmetic
+happens in libwhitomo_b200.so, reached through the C ABI in include/whitomo_b200.h.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _capi.EngineError("whitomo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Spectrum(object):
+    """Device tables of the polychromatic model (constructor state of WhiteProjection,
+    src/white_projection.py:23-73).  ``source`` must already be normalised by its integral."""
+
+    def __init__(self, source, widths, absorptions, pixel_size):
+        _require_cuda()
+        self.lib = _capi.load()
+        source = np.ascontiguousarray(source, dtype=np.float64)
+        widths = np.ascontiguousarray(widths, dtype=np.float64)
+        absorptions = np.ascontiguousarray(absorptions, dtype=np.float64)
+        self.K, self.E = absorptions.shape
+        assert source.shape == (self.E,) and widths.shape == (self.E,)
+        h = ctypes.c_void_p()
+        dp = ctypes.POINTER(ctypes.c_double)
+        _capi.check(self.lib.wt_spectrum_create(self.K, self.E, source.ctypes.data_as(dp), widths.ctypes.data_as(dp),
+                                                absorptions.ctypes.data_as(dp), float(pixel_size), ctypes.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.wt_spectrum_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Projector(object):
+    def __init__(self, rows, cols, ndet, angles, det_width=1.0, device=None):
+        _require_cuda()
+        self.lib = _capi.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.rows, self.cols, self.ndet = int(rows), int(cols), int(ndet)
+        self.det_width = float(det_width)
+        self.angles = np.ascontiguousarray(np.asarray(angles, dtype=np.float64).astype(np.float32))
+        self.nangles = int(self.angles.shape[0])
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.wt_geom_create(self.rows, self.cols, self.ndet, self.det_width,
+                                                self.angles.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                                self.nangles, ctypes.byref(h)))
+        self.handle = h
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.wt_geom_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- shapes -------------------------------------------------------------------------------
+    @property
+    def vol_shape(self):
+        return (self.rows, self.cols)
+
+    @property
+    def sino_shape(self):
+        return (self.nangles, self.ndet)
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _as_images(self, t, shape):
+        """accept (..., *shape) float32 CUDA tensors; return (contiguous (n, *shape) view, leading dims)"""
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t, dtype=np.float32))
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        if t.dtype != torch.float32:
+            t = t.float()
+        if tuple(t.shape[-2:]) != tuple(shape):
+            raise ValueError("expected trailing shape %s, got %s" % (shape, tuple(t.shape)))
+        lead = tuple(t.shape[:-2])
+        return t.reshape((-1,) + tuple(shape)).contiguous(), lead
+
+    # ---- operators ------------------------------------------------------------------------------
+    def fp(self, vol, out=None):
+        """p = W x.  vol (..., rows, cols) -> (..., nangles, ndet) float32 on the device."""
+        v, lead = self._as_images(vol, self.vol_shape)
+        n = v.shape[0]
+        if out is None:
+            out = torch.empty((n,) + self.sino_shape, dtype=torch.float32, device=self.device)
+        nbytes = self.lib.wt_workspace_bytes(self.handle, n)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, _ptr(ws), nbytes, _stream()))
+        return out.reshape(lead + self.sino_shape)
+
+    def bp(self, sino, out=None, angle_range=None):
+        """g = W^T q (exact transpose).  sino (..., nangles, ndet) -> (..., rows, cols)."""
+        s, lead = self._as_images(sino, self.sino_shape)
+        n = s.shape[0]
+        if out is None:
+            out = torch.empty((n,) + self.vol_shape, dtype=torch.float32, device=self.device)
+        a0, a1 = (0, self.nangles) if angle_range is None else angle_range
+        nbytes = self.lib.wt_workspace_bytes(self.handle, n)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_bp(self.handle, _ptr(s), _ptr(out), n, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
+        return out.reshape(lead + self.vol_shape)
+
+    def sirt(self, sino, n_iters=100):
+        """ASTRA-style SIRT from x0 = 0; sino (..., nangles, ndet) -> (..., rows, cols)."""
+        s, lead = self._as_images(sino, self.sino_shape)
+        n = s.shape[0]
+        out = torch.empty((n,) + self.vol_shape, dtype=torch.float32, device=self.device)
+        nbytes = self.lib.wt_sirt_workspace_bytes(self.handle, n)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_sirt(self.handle, _ptr(s), _ptr(out), n, int(n_iters), _ptr(ws), nbytes, _stream()))
+        return out.reshape(lead + self.vol_shape)
+
+    def ramp_filter(self, sino):
+        """Fourier ramp of ASTRA's CPU FBP: zero-pad to pow2 >= 2D, multiply bin i by 2 i / zp."""
+        s, lead = self._as_images(sino, self.sino_shape)
+        zp = 1
+        while zp < 2 * self.ndet:
+            zp <<= 1
+        f = torch.fft.rfft(s, n=zp, dim=-1)
+        ramp = (2.0 * torch.arange(zp // 2 + 1, device=self.device, dtype=torch.float32)) / zp
+        out = torch.fft.irfft(f * ramp, n=zp, dim=-1)[..., :self.ndet].contiguous()
+        return out.reshape(lead + self.sino_shape)
+
+    def fbp(self, sino):
+        """x = pi/(2A) * W^T ramp(p)  (cpu_fbp, src/astra_proxy.py:87-102)."""
+        return self.bp(self.ramp_filter(sino)) * (np.pi / (2.0 * self.nangles))
+
+    def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True):
+        """Fused white-beam forward model + residual (wt_white_fp).  conc (S, K, rows, cols) or (K, rows, cols).
+        Returns (intensity (S,A,D) | None, qmu (S,K,A,D) | None, loss (S,) float64 | None)."""
+        c, lead = self._as_images(conc, self.vol_shape)
+        K = spectrum.K
+        if c.shape[0] % K:
+            raise ValueError("conc must hold a multiple of K=%d images" % K)
+        S = c.shape[0] // K
+        m = None
+        if meas is not None:
+            m, _ = self._as_images(meas, self.sino_shape)
+            if m.shape[0] != S:
+                raise ValueError("meas must hold one sinogram per slice")
+        inten = torch.empty((S,) + self.sino_shape, dtype=torch.float32, device=self.device) if want_intensity else None
+        qmu = torch.empty((S, K) + self.sino_shape, dtype=torch.float32, device=self.device) if want_qmu else None
+        loss = torch.empty((S,), dtype=torch.float64, device=self.device) if want_loss else None
+        nbytes = self.lib.wt_workspace_bytes(self.handle, S * K)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_white_fp(self.handle, spectrum.handle, _ptr(c), _ptr(m), _ptr(inten), _ptr(qmu),
+                                         _ptr(loss), S, _ptr(ws), nbytes, _stream()))
+        return inten, qmu, loss
+
+    def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, lower_only=False, want_penalty=False):
+        """In-place fused box-barrier gradient step (wt_barrier_update).  x, grad: (S, K, rows, cols)."""
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            raise ValueError("x must be a contiguous float32 tensor on %s" % self.device)
+        g = grad if (grad.dtype == torch.float32 and grad.is_contiguous()) else grad.float().contiguous()
+        if x.dim() == 2:
+            S, K = 1, 1
+        elif x.dim() == 3:
+            S, K = 1, x.shape[0]
+        else:
+            S, K = x.shape[0], x.shape[1]
+        npix = x.shape[-1] * x.shape[-2]
+        pen = torch.empty((S,), dtype=torch.float64, device=self.device) if want_penalty else None
+        nbytes = self.lib.wt_workspace_bytes(self.handle, S * K)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_barrier_update(_ptr(x), _ptr(g), S, K, npix, float(alpha), float(beta_reg), float(t),
+                                               float(reg_w), int(bool(lower_only)), _ptr(pen), _ptr(ws), nbytes,
+                                               _stream()))
+        return pen
