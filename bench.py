@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Headline benchmark of the hot path (BASELINE.json): FP+BP GUPS and barrier iterations/s on the
+2048^2 x 1800-angle white-beam log-barrier configuration (configs[3], "C4"), slice-sharded over N GPUs.
+
+A "step" is ONE inner iteration of the white-beam barrier method (src/barrier_method.py:163-206 with the
+goal of src/white_projection.py:116-127) on a resident batch of slices per GPU:
+    fused white-beam FP (K=2 projections + exp/spectrum-sum/residual/q*mu, E=64)  ->  K BP  ->  fused K3 update.
+`value` counts the pixel*angle updates of those K FP + K BP (N^2 * A each) for all slices of all ranks.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun by the driver)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port on the box's host cores)
+
+Prints ONE JSON line (rank 0).  The CPU oracle (oracle/) is only ever executed for the cpu_baseline /
+--impl reference numbers, never for the measured value.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N, A, K, E = 2048, 1800, 2, 64
+D = int(np.sqrt(2) * N + 1)
+METRIC = "fp_bp_gups"
+UNIT = "GUPS (1e9 pixel*angle updates/s, K FP + K BP of each barrier iteration)"
+WORKLOAD = "C4: white-beam log-barrier iteration, 2048x2048 slices, 1800 angles, D=2897, K=2, E=64"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """samples SM clock + throttle reasons of one GPU with NVML while the timed region runs"""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+            return self
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU side (oracle port): used for cpu_baseline and for --impl reference only
+# --------------------------------------------------------------------------------------------------
+def cpu_grad_sample(n_angles_sample, threads):
+    """One func+grad evaluation of the reference's white-beam model (src/white_projection.py:86-127: K FP,
+    numpy float64 point-wise work over (rays, E), K BP) on ONE 2048^2 slice restricted to every
+    (1800 // n_angles_sample)-th angle of the C4 geometry.  Returns (seconds, updates)."""
+    import oracle
+    from oracle import white as ow
+    from whitomo_b200 import phantoms
+    grid, source, ea, pix = phantoms.synth_spectrum(E, N)
+    angles = np.linspace(0, np.pi, A)[:: max(1, A // n_angles_sample)][:n_angles_sample]
+    geom = oracle.Geometry(N, N, D, angles)
+    wo = ow.WhiteOracle(source, pix, ea, grid, (N, N), geometry=geom)
+    wo.FP = lambda x: oracle.fp(geom, x, threads=threads)
+    wo.BP = lambda x: oracle.bp(geom, x, threads=threads)
+    gt = phantoms.two_discs(N)
+    wo.calc_sinogram_with_gt(gt)
+    c = np.full(gt.shape, 0.15)
+    t0 = time.perf_counter()
+    wo.grad(c)
+    dt = time.perf_counter() - t0
+    return dt, 2.0 * K * N * N * len(angles)
+
+
+def cpu_baseline_block(budget_s=20.0):
+    """bounded single-thread sample (ASTRA's 2D CPU algorithms are single-threaded)"""
+    import oracle
+    oracle.build()
+    dt, upd = cpu_grad_sample(8, 1)                       # probe
+    n_s = int(max(8, min(A, 8 * budget_s / max(dt, 1e-3))))
+    n_s = min(n_s, 225)
+    dt, upd = cpu_grad_sample(n_s, 1)
+    return {"value": upd / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "one func+grad (K=2 FP + K=2 BP + numpy white-beam model, E=64) on one 2048^2 slice, "
+                      "%d of the 1800 angles, single thread, %.1f s" % (n_s, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = oracle.num_threads()
+    probe = max(32, 2 * threads)
+    dt, _ = cpu_grad_sample(probe, threads)               # probe, also warms the page cache
+    n_s = int(max(probe, min(A, probe * 6.0 / max(dt, 1e-3))))   # ~6 s per step
+    for _ in range(min(args.warmup, 1)):
+        cpu_grad_sample(n_s, threads)
+    times, upd = [], 0.0
+    for _ in range(args.steps):
+        dt, upd = cpu_grad_sample(n_s, threads)
+        times.append(dt)
+    t = float(np.mean(times))
+    val = upd / t / 1e9
+    sample = ("one func+grad per step on one 2048^2 slice, %d of the 1800 angles, %d host threads (pthreads over "
+              "angles), numpy float64 white-beam model; the reference's loop spends 3K FP + K BP per iteration, "
+              "only K FP + K BP are counted here" % (n_s, threads))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "barrier_iters_per_s": 1.0 / t * (n_s / float(A)),
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU side
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from whitomo_b200 import phantoms, _capi
+    from whitomo_b200.projector import Projector, Spectrum
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.slices                                   # resident slices per GPU per step (weak scaling)
+    proj = Projector(N, N, D, np.linspace(0, np.pi, A), device=dev)
+    grid, source, ea, pix = phantoms.synth_spectrum(E, N)
+    source = source / np.sum(source * grid[:, 1])
+    spec = Spectrum(source, grid[:, 1], ea, pix)
+
+    # synthetic stack: slice-dependent two-disc phantoms; each rank owns its own slice range
+    gt = torch.stack([torch.from_numpy(phantoms.two_discs(N, z=(rank * S + s) / float(max(1, world * S))))
+                      for s in range(S)]).to(dev)
+    meas, _, _ = proj.white_fp(spec, gt, want_qmu=False, want_loss=False)
+    del gt
+    gen = torch.Generator(device=dev).manual_seed(12345 + rank)
+    x0 = (0.15 + 0.05 * (torch.rand((S, K, N, N), device=dev, generator=gen) - 0.5)).contiguous()
+    x = x0.clone()
+    alpha, beta, t_bar, ir_beta = 1.0, 1.0, 0.1, 0.05    # src/barrier_method_gogo.py:184-192
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def step(timed):
+        m = [ev() for _ in range(4)] if timed else None
+        if timed:
+            m[0].record()
+        _, qmu, loss = proj.white_fp(spec, x, meas=meas, want_intensity=False)
+        if timed:
+            m[1].record()
+        g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+        if timed:
+            m[2].record()
+        pen = proj.barrier_update(x, g, alpha, beta, t_bar, reg_w=ir_beta, want_penalty=True)
+        if timed:
+            m[3].record()
+            marks.append(m)
+        return loss, pen
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sync_all()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        loss, pen = step(True)
+    e1.record()
+    sync_all()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    final_loss = float(loss.sum().item())
+    if not np.isfinite(final_loss):
+        raise SystemExit("bench.py: non-finite data-fidelity loss after the timed region")
+
+    # ---- end-to-end arm: host buffers in, host buffers out, through the same public calls ------------
+    h_x = torch.empty((S, K, N, N), dtype=torch.float32).pin_memory()
+    h_x.copy_(x0.cpu())
+    h_meas = torch.empty(meas.shape, dtype=torch.float32).pin_memory()
+    h_meas.copy_(meas.cpu())
+    h_out = torch.empty((S, K, N, N), dtype=torch.float32).pin_memory()
+    h_loss = torch.empty((S,), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        xd = h_x.to(dev, non_blocking=True)
+        md = h_meas.to(dev, non_blocking=True)
+        _, qmu, l_ = proj.white_fp(spec, xd, meas=md, want_intensity=False)
+        g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+        p_ = proj.barrier_update(xd, g, alpha, beta, t_bar, reg_w=ir_beta, want_penalty=True)
+        h_out.copy_(xd, non_blocking=True)
+        h_loss.copy_(l_ + p_, non_blocking=True)
+
+    for _ in range(min(2, args.warmup)):
+        e2e_step()
+    sync_all()
+    f0, f1 = ev(), ev()
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    sync_all()
+    e2e_elapsed = f0.elapsed_time(f1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(tt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    upd_per_step = 2.0 * K * N * N * A * S * world          # K FP + K BP per slice, all ranks
+    value = upd_per_step * args.steps / elapsed / 1e9
+    t_fp = float(np.mean([m[0].elapsed_time(m[1]) for m in marks])) * 1e-3
+    t_bp = float(np.mean([m[1].elapsed_time(m[2]) for m in marks])) * 1e-3
+    t_up = float(np.mean([m[2].elapsed_time(m[3]) for m in marks])) * 1e-3
+    hbm, which = peaks()
+    # algorithmic bytes per launch: fused white FP reads K*N^2 + A*D (meas), writes K*A*D (q*mu)
+    fp_bytes = 4.0 * (K * N * N + A * D + K * A * D) * S
+    bp_bytes = 4.0 * (K * A * D + K * N * N) * S
+    up_bytes = 12.0 * K * N * N * S
+    roof = lambda b, tm: {"bound": "hbm", "achieved": b / tm / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": b / tm / 1e9 / hbm, "traffic": None, "peak_source": which}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "slices_per_gpu_per_step": S, "images_per_step": S * K * world,
+                   "l2": "inputs larger than L2 (%.0f MB of concentrations + %.0f MB of q*mu per step per GPU)"
+                         % (4e-6 * S * K * N * N, 4e-6 * S * K * A * D),
+                   "parallelism": "slices sharded over %d rank(s), no data-path collective" % world},
+        "barrier_iters_per_s": S * world * args.steps / elapsed,
+        "fp_gups": K * N * N * A * S / t_fp / 1e9, "bp_gups": K * N * N * A * S / t_bp / 1e9,
+        "kernel_ms": {"white_fp": t_fp * 1e3, "bp": t_bp * 1e3, "barrier_update": t_up * 1e3},
+        "roofline": dict(roof(fp_bytes, t_fp), kernel="fp_kernel<4, white epilogue> (dominant: %.0f%% of the step)"
+                         % (100 * t_fp / (t_fp + t_bp + t_up)),
+                         note="gather/stencil kernel with ~N-fold on-chip reuse: bound by L1/LSU issue, not HBM "
+                              "(SURVEY 8d: compulsory-bytes ceiling of the HBM fraction is ~0.4%)"),
+        "roofline_bp": dict(roof(bp_bytes, t_bp), kernel="bp_kernel<4> (TMA-staged gather)"),
+        "roofline_update": dict(roof(up_bytes, t_up), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3)"),
+        "e2e": {"value": upd_per_step * args.steps / e2e_elapsed / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(h_x.numel() * 4 + h_meas.numel() * 4) * world,
+                "d2h_bytes_per_step": int(h_out.numel() * 4 + h_loss.numel() * 8) * world,
+                "ms_per_step": e2e_elapsed / args.steps * 1e3,
+                "what": "pinned host concentrations + measured sinograms -> device, one barrier iteration through "
+                        "Projector.white_fp/bp/barrier_update, updated concentrations + loss -> host"},
+        "gpu_launches": 7 * args.steps,
+        "clocks": clocks,
+        "loss_after": final_loss,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline_block()
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slices", type=int, default=8, help="resident slices per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,11 +54,13 @@ size_t wt_workspace_bytes(const wt_geom *g, int nimages);
 int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws, size_t ws_bytes,
           void *stream);
 
-/* g = W^T q (exact transpose).  Replaces gpu_bp (src/astra_proxy.py:52-66: ASTRA 'BP').
- * sino (nimages, nangles, ndet) -> vol (nimages, rows, cols).  Only angles [angle_begin, angle_end)
- * contribute (the angle-range split of one oversized slice); pass 0, nangles for the full operator. */
+/* g = scale * W^T q (exact transpose).  Replaces gpu_bp (src/astra_proxy.py:52-66: ASTRA 'BP'); scale = 1 is
+ * the plain operator, -1 gives the white-beam gradient sign (src/white_projection.py:112), pi/(2A) the FBP
+ * normalisation (src/astra_proxy.py:87-102).  sino (nimages, nangles, ndet) -> vol (nimages, rows, cols).
+ * Only angles [angle_begin, angle_end) contribute (the angle-range split of one oversized slice); pass
+ * 0, nangles for the full operator. */
 int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end,
-          void *ws, size_t ws_bytes, void *stream);
+          float scale, void *ws, size_t ws_bytes, void *stream);
 
 /* x = SIRT(p, n_iters), x0 = 0.  Replaces cpu_sirt (src/astra_proxy.py:69-84: ASTRA 'SIRT').
  * sino (nimages, nangles, ndet) -> vol (nimages, rows, cols). */
@@ -85,16 +87,36 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
                 float *intensity, float *qmu, double *loss, int nslices, void *ws, size_t ws_bytes,
                 void *stream);
 
-/* Fused box-barrier gradient step (one inner iteration of barrier_method with the gogo constraints):
- *   grad = g + beta_reg*reg_w*d|c0 c1|/dc + beta_reg*t*(-1/x + 1/(1-x));  x <- clip(x - alpha*grad, 0, 1)
- * Replaces src/barrier_method.py:164-206 with the (f,g,proj) tuples of src/barrier_method_gogo.py:79-94
- * and calc_uneq_reg_grad (src/white_rec.py:180-186).  x, g: (nslices, K, rows, cols); x updated in place.
- * reg_w = 0 disables the |c0 c1| regulariser (requires K == 2 otherwise); lower_only != 0 keeps only the
- * x >= 0 barrier and clips to [0, +inf) (the mono MAR 'morezero' constraint, teeth_recon/experiments.py:704-706).
- * penalty (nslices, float64, optional): sum beta_reg*reg(x') + beta_reg*t*phi(x') at the NEW x, the terms
- * barrier_method adds to the loss for its early-stop test (src/barrier_method.py:208-213). */
-int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, float alpha,
-                      float beta_reg, float t, float reg_w, int lower_only, double *penalty, void *ws,
+/* K3: fused gradient-combine + regularisers + log-barrier + step + projection, one streaming pass.
+ * Replaces, per inner iteration,
+ *   - src/barrier_method.py:164-206 with the (f, g, proj) box tuples of src/barrier_method_gogo.py:79-94 and
+ *     the |c0 c1| regulariser (calc_uneq_reg_grad, src/white_rec.py:180-186);
+ *   - the 'morezero' constraint of the mono MAR run (teeth_recon/experiments.py:704-706) with lower_only;
+ *   - the plain gradient step of Iteration (src/white_rec.py:223-242) with t = 0, reg_w = triv_w = 1.
+ * For every slice s, element k, pixel i (x, grad: (nslices, K, npix), x updated in place):
+ *   G  = grad + beta_reg*(reg_w * d|c0 c1|/dc_k + triv_w * c(c(4c-3)+1)) + beta_reg*t*(-1/x [+ 1/(1-x)])
+ *   x' = x - alpha*G          if bit k of elem_mask is set and the slice is active
+ *   x' = clip(x', 0, 1 | +inf) if mode != WT_UPD_STEP_ONLY
+ * t == 0 drops the barrier terms altogether (no 0*inf).  mode WT_UPD_CLIP_ONLY only projects.
+ * active (nslices bytes, optional): slices with active[s] == 0 are left untouched (per-slice early stop).
+ * penalty (nslices float64, optional): sum_k,i beta_reg*reg_w*|c0 c1| + beta_reg*t*phi(x') at the NEW x -- the
+ * terms barrier_method adds to f(x) for its early-stop test (src/barrier_method.py:208-213); +inf on the boundary. */
+#define WT_UPD_STEP_CLIP 0
+#define WT_UPD_STEP_ONLY 1
+#define WT_UPD_CLIP_ONLY 2
+typedef struct {
+    float alpha;
+    float beta_reg;
+    float t;
+    float reg_w;
+    float triv_w;
+    int lower_only;
+    int mode;
+    unsigned elem_mask;
+} wt_update_params;
+
+int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix,
+                      const wt_update_params *prm, const unsigned char *active, double *penalty, void *ws,
                       size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus

@@ -187,9 +187,12 @@ typedef struct {
 static void *mt_run(void *arg)
 {
     mt_job *j = (mt_job *)arg;
-    /* interleaved blocks of 4 angles balance the vertical/horizontal halves across threads */
-    for (int a = j->tid * 4; a < j->g->nangles; a += j->nth * 4) {
-        int a1 = a + 4 < j->g->nangles ? a + 4 : j->g->nangles;
+    /* interleaved blocks of <= 4 angles balance the vertical/horizontal halves across threads */
+    int blk = j->g->nangles / (j->nth * 4);
+    if (blk < 1) blk = 1;
+    if (blk > 4) blk = 4;
+    for (int a = j->tid * blk; a < j->g->nangles; a += j->nth * blk) {
+        int a1 = a + blk < j->g->nangles ? a + blk : j->g->nangles;
         walk(j->g, a, a1, j->mode, j->vol, j->sino);
     }
     return NULL;

@@ -1,0 +1,173 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol,
+the `astra` shim builds the reference's geometry dicts, and the py3 host mirrors of barrier_method /
+HoughBarrier / white_rec reproduce the golden outputs of the reference's own modules when their FP/BP
+closures are backed by the oracle (the product never imports the oracle; these tests inject it)."""
+import ctypes
+import os
+import re
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import white as ow, barrier as ob
+from conftest import rel_l2, ROOT
+
+
+def test_capi_loads_and_exports_every_declared_symbol():
+    from whitomo_b200 import _capi
+    lib = _capi.load()
+    hdr = open(os.path.join(ROOT, "include", "whitomo_b200.h")).read()
+    declared = set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.wt_version() >= 100
+    assert ctypes.sizeof(_capi.UpdateParams) == 32
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.wt_geom_dims(None, None, None, None, None) == -1
+    assert b"null geometry" in lib.wt_last_error()
+    assert lib.wt_workspace_bytes(None, 4) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from whitomo_b200._capi import EngineError
+    from whitomo_b200.projector import Projector
+    with pytest.raises(EngineError):
+        Projector(8, 8, 12, np.linspace(0, np.pi, 4))
+    from whitomo_b200 import astra_proxy as ap
+    pg = ap.astra.create_proj_geom("parallel", 1.0, 12, np.linspace(0, np.pi, 4))
+    vg = ap.astra.create_vol_geom(8, 8)
+    with pytest.raises(EngineError):
+        ap.gpu_fp(pg, vg, np.zeros((8, 8)), 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "whitomo_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+
+
+def test_astra_shim_geometry_dicts():
+    from whitomo_b200 import astra_proxy as ap
+    astra = ap.astra
+    ang = np.linspace(0, np.pi, 7)
+    pg = astra.create_proj_geom("parallel", 1.0, 15, ang)
+    assert pg["type"] == "parallel" and pg["DetectorCount"] == 15 and pg["DetectorWidth"] == 1.0
+    assert np.array_equal(pg["ProjectionAngles"], ang)
+    for vg in (astra.create_vol_geom(10, 12), astra.create_vol_geom((10, 12)), astra.create_vol_geom(*(10, 12))):
+        assert vg["GridRowCount"] == 10 and vg["GridColCount"] == 12
+        assert vg["option"]["WindowMinX"] == -6 and vg["option"]["WindowMaxY"] == 5
+    assert astra.create_vol_geom(9)["GridColCount"] == 9
+    pickle.loads(pickle.dumps((pg, vg)))                      # teeth_recon/experiments.py:284-285
+    with pytest.raises(NotImplementedError):
+        astra.create_proj_geom("fanflat", 1.0, 15, ang, 1, 1)
+    p2 = ap.AstraProxy(2)
+    assert (p2.fp_algo_name, p2.bp_algo_name, p2.sirt_algo_name, p2.fbp_algo_name) == ("FP", "BP", "SIRT", "FBP")
+    assert p2.dart_mask_name == "DARTMASK"
+    with pytest.raises(NotImplementedError):
+        ap.AstraProxy(4)
+    assert astra.astra_dict("FP") == {"type": "FP"}
+    i = astra.data2d.create("-vol", vg, np.ones((10, 12)))
+    assert astra.data2d.get(i).dtype == np.float32
+    with pytest.raises(ValueError):
+        astra.data2d.create("-sino", pg, np.ones((3, 3)))
+    astra.data2d.delete(i)
+
+
+def test_barrier_method_mirror_vs_reference_golden_white(golden, capsys):
+    from whitomo_b200 import barrier_method as bm, white_rec
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    wo = ow.WhiteOracle(z["source"], float(z["pixel_size"]), z["ea"], z["grid"], (n, n), n_angles=na)
+    wo.calc_sinogram_with_gt(z["gt"])
+    ir = float(z["ir_beta"])
+    reg = (lambda x: ir * np.abs(x[0] * x[1]), lambda x: ir * white_rec.calc_uneq_reg_grad(x))
+    nonneg = (lambda x: -x, lambda x: -np.ones_like(x), lambda x: np.clip(x, 0, x.max()))
+    le_one = (lambda x: x - 1, lambda x: np.ones_like(x), lambda x: np.clip(x, x.min(), 1))
+    p = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+    seen = []
+    ans, stats = bm.barrier_method(z["x0"].copy(), (wo.func, wo.grad), reg_dict={"ineq_reg": reg},
+                                   ineq_dict={"conc_non_negative": nonneg, "conc_less_than_one": le_one},
+                                   add_stat_cb=seen.append, **p)
+    assert stats == []
+    assert rel_l2(ans, z["ans"]) < 1e-12
+    goal, regs, bfs = seen[0]
+    assert set(regs) == {"ineq_reg"} and set(bfs) == {"conc_non_negative", "conc_less_than_one"}
+    assert goal.x.shape == z["x0"].shape and np.isscalar(float(goal.func))
+
+
+def test_barrier_method_infeasible_start_returns_none(capsys):
+    from whitomo_b200 import barrier_method as bm
+    never = (lambda x: x + 1.0, lambda x: np.ones_like(x), lambda x: x)        # x + 1 <= 0 is never met by proj
+    x, stats = bm.barrier_method(np.ones(4), (lambda x: 0.0, lambda x: np.zeros_like(x)), ineq_dict={"c": never},
+                                 n_iter=1, n_biter=1)
+    assert stats is None and np.array_equal(x, np.ones(4))
+    assert "feasibility projection unsuccesfull" in capsys.readouterr().out
+
+
+def test_hough_barrier_mirror_vs_reference_golden_mar(golden, capsys):
+    from whitomo_b200 import barrier_method as bm
+    from whitomo_b200.barrier import HoughBarrier
+    z = golden("barrier_mar")
+    n, na = int(z["n"]), int(z["n_angles"])
+    g = oracle.Geometry.standard(n, na)
+    FP = lambda x: oracle.fp(g, x.reshape(n, n)).flatten()
+    BP = lambda x: oracle.bp(g, x.reshape(g.sino_shape)).flatten()
+    i0, bound = float(z["i0"]), float(z["bound"])
+    r, m = ob.ray_transform_from_projection(z["projections"].copy(), bound, i0)
+    m, b = m.flatten(), r.flatten()
+    bound_log = np.log(i0) - np.log(bound)
+    b[m] = bound_log
+    bound_log *= 0.95
+    n_good = m.size - np.sum(m)
+
+    def cost(x):
+        d = FP(x) - b
+        d[m] = 0
+        d /= n_good
+        return np.sum(d ** 2)
+
+    def grad(x):
+        d = FP(x) - b
+        d[m] = 0
+        d /= n_good
+        return 2.0 * BP(d)
+
+    hb = HoughBarrier(FP, BP, m, bound_log, r)
+    morezero = (lambda x: -x, lambda x: -np.ones_like(x), lambda x: np.clip(x, 0, x.max()))
+    x0 = 1e-2 + np.zeros((n, n), dtype="float32").flatten()
+    ans, _ = bm.barrier_method(x0, (cost, grad), ineq_dict={"bound": hb, "morezero": morezero}, n_iter=200,
+                               n_biter=int(z["n_biter"]), t0=0.2, t_step=0.2, beta_reg=1.0, alpha=0.1, max_iter=400,
+                               do_alpha_decay=False)
+    assert rel_l2(ans.reshape(n, n), z["ans"]) < 1e-6
+    assert hb.num_feval > 0 and hb.num_geval > 0
+
+
+def test_white_rec_helpers_match_oracle():
+    from whitomo_b200 import white_rec
+    c = np.random.default_rng(0).uniform(-0.2, 1.2, (2, 9, 11))
+    assert np.array_equal(white_rec.calc_uneq_reg_grad(c), ow.calc_uneq_reg_grad(c))
+    assert np.allclose(white_rec.calc_triv_conc_grad(c), ow.calc_triv_conc_grad(c), rtol=1e-15)
+    torch = pytest.importorskip("torch")
+    ct = torch.from_numpy(c)
+    assert np.array_equal(white_rec.calc_uneq_reg_grad(ct).numpy(), ow.calc_uneq_reg_grad(c))
+
+
+def test_synthetic_inputs():
+    from whitomo_b200 import phantoms
+    grid, src, ea, pix = phantoms.synth_spectrum(2, 256)
+    assert np.array_equal(grid, np.array([[2.5, 0.005], [10, 0.005]])) and pix == 1e-6     # src/phantoms.py:159-181
+    grid, src, ea, pix = phantoms.synth_spectrum(64, 512)
+    assert grid.shape == (64, 2) and np.isclose(grid[8, 0], 2.5) and np.isclose(grid[38, 0], 10.0)
+    assert np.allclose(ea[:, 8], [4000, 300]) and np.allclose(ea[:, 38], [302.04159662, 2000])
+    c = phantoms.two_discs(256)
+    assert c.shape == (2, 256, 256) and abs(c[0].sum() - 7845) < 60 and abs(c[1].sum() - 1257) < 30
+    t = phantoms.tooth_phantom(64)
+    assert np.allclose(np.unique(t), [0, phantoms.CA_LEVEL, phantoms.AU_LEVEL])

@@ -18,7 +18,7 @@ SIGNATURES = {
     "wt_geom_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "wt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "wt_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
-    "wt_bp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "wt_bp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "wt_sirt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "wt_sirt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "wt_spectrum_create": (c_int, [c_int, c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_double),
@@ -26,9 +26,19 @@ SIGNATURES = {
     "wt_spectrum_destroy": (None, [c_void_p]),
     "wt_white_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                             c_void_p, c_size_t, c_void_p]),
-    "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_float, c_float, c_float, c_float,
-                                  c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
 }
+
+
+
+class UpdateParams(ctypes.Structure):
+    """wt_update_params of include/whitomo_b200.h"""
+    _fields_ = [("alpha", c_float), ("beta_reg", c_float), ("t", c_float), ("reg_w", c_float), ("triv_w", c_float),
+                ("lower_only", c_int), ("mode", c_int), ("elem_mask", ctypes.c_uint)]
+
+
+UPD_STEP_CLIP, UPD_STEP_ONLY, UPD_CLIP_ONLY = 0, 1, 2
 
 _lib = None
 

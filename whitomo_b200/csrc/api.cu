@@ -266,8 +266,8 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws
     return run_fp(g, vol, nimages, 0, g->nangles, vn, vt, epi, (cudaStream_t)stream);
 }
 
-int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, void *ws,
-          size_t ws_bytes, void *stream) {
+int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, float scale,
+          void *ws, size_t ws_bytes, void *stream) {
     if (!g || !vol || !sino || !ws) return invalid("wt_bp: null pointer");
     if (nimages <= 0) return invalid("wt_bp: nimages must be positive");
     if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_bp: bad angle range");
@@ -276,7 +276,7 @@ int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angl
     float *sp = cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
     HBpStore epi;
     epi.vol = vol;
-    epi.scale = 1.0f;
+    epi.scale = scale;
     epi.img = (size_t)g->rows * g->cols;
     return run_bp(g, sino, nimages, angle_begin, angle_end, sp, epi, (cudaStream_t)stream);
 }
@@ -388,11 +388,13 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
     return WT_OK;
 }
 
-int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, float alpha, float beta_reg,
-                      float t, float reg_w, int lower_only, double *penalty, void *ws, size_t ws_bytes, void *stream) {
-    if (!x || !grad) return invalid("wt_barrier_update: null pointer");
+int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, const wt_update_params *prm,
+                      const unsigned char *active, double *penalty, void *ws, size_t ws_bytes, void *stream) {
+    if (!x || !prm) return invalid("wt_barrier_update: null pointer");
+    if (!grad && prm->mode != WT_UPD_CLIP_ONLY) return invalid("wt_barrier_update: grad is required unless mode is WT_UPD_CLIP_ONLY");
     if (nslices <= 0 || n_elements <= 0 || n_elements > 4 || npix == 0) return invalid("wt_barrier_update: bad sizes (1 <= K <= 4)");
-    if (reg_w != 0.0f && n_elements != 2) return invalid("wt_barrier_update: the |c0 c1| regulariser needs K == 2");
+    if (prm->reg_w != 0.0f && n_elements != 2) return invalid("wt_barrier_update: the |c0 c1| regulariser needs K == 2");
+    if (prm->mode < 0 || prm->mode > 2) return invalid("wt_barrier_update: bad mode");
     double *partial = nullptr;
     if (penalty) {
         if (!ws || ws_bytes < (size_t)nslices * UPD_BLOCKS_PER_SLICE * sizeof(double)) { g_err = "wt_barrier_update: workspace too small"; return WT_ERR_WORKSPACE; }
@@ -403,10 +405,10 @@ int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, 
     if (bx > UPD_BLOCKS_PER_SLICE) bx = UPD_BLOCKS_PER_SLICE;
     dim3 grid(bx, nslices);
     switch (n_elements) {
-    case 1: barrier_update_kernel<1><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
-    case 2: barrier_update_kernel<2><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
-    case 3: barrier_update_kernel<3><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
-    default: barrier_update_kernel<4><<<grid, 256, 0, st>>>(x, grad, npix, alpha, beta_reg, t, reg_w, lower_only, partial); break;
+    case 1: barrier_update_kernel<1><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
+    case 2: barrier_update_kernel<2><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
+    case 3: barrier_update_kernel<3><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
+    default: barrier_update_kernel<4><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
     }
     WT_CUDA(cudaGetLastError());
     if (penalty) {

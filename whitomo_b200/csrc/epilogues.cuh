@@ -172,44 +172,60 @@ constexpr int UPD_BLOCKS_PER_SLICE = 296;  // 2 CTAs per SM worth of partials pe
 
 template <int K>
 __global__ void __launch_bounds__(256) barrier_update_kernel(float *__restrict__ x, const float *__restrict__ grad,
-                                                             size_t npix, float alpha, float beta, float t, float reg_w,
-                                                             int lower_only, double *partial) {
+                                                             size_t npix, wt_update_params prm,
+                                                             const unsigned char *__restrict__ active, double *partial) {
     const size_t slice = blockIdx.y;
     float *xs = x + slice * K * npix;
-    const float *gs = grad + slice * K * npix;
+    const float *gs = grad ? grad + slice * K * npix : nullptr;
+    const bool act = (!active || active[slice]) && prm.mode != WT_UPD_CLIP_ONLY;
+    const bool clip = prm.mode != WT_UPD_STEP_ONLY && (!active || active[slice]);
+    const bool use_reg = (K == 2) && prm.reg_w != 0.0f;
+    const bool use_bar = prm.t != 0.0f;
+    const float bt = prm.beta_reg * prm.t;
     double pen = 0.0;
-    const float bt = beta * t;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         float xv[K], xn[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) xv[k] = xs[k * npix + i];
         float sgn = 0.0f;
-        if (K == 2 && reg_w != 0.0f) {
+        if (use_reg) {
             const float pr = xv[0] * xv[1];
             sgn = pr > 0.0f ? 1.0f : (pr < 0.0f ? -1.0f : 0.0f);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float gt = __ldg(gs + k * npix + i);
-            if (K == 2 && reg_w != 0.0f) gt += beta * (reg_w * (xv[1 - k] * sgn));
-            gt += bt * (-1.0f / xv[k]);
-            if (!lower_only) gt += bt * (1.0f / (1.0f - xv[k]));
-            float v = xv[k] - alpha * gt;
-            v = fmaxf(v, 0.0f);
-            if (!lower_only) v = fminf(v, 1.0f);
+            float v = xv[k];
+            if (act && ((prm.elem_mask >> k) & 1u)) {
+                float gt = __ldg(gs + k * npix + i);
+                float rg = 0.0f;
+                if (use_reg) rg = prm.reg_w * (xv[K == 2 ? 1 - k : 0] * sgn);
+                if (prm.triv_w != 0.0f) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
+                gt += prm.beta_reg * rg;
+                if (use_bar) {
+                    gt += bt * (-1.0f / v);
+                    if (!prm.lower_only) gt += bt * (1.0f / (1.0f - v));
+                }
+                v = v - prm.alpha * gt;
+            }
+            if (clip) {
+                v = fmaxf(v, 0.0f);
+                if (!prm.lower_only) v = fminf(v, 1.0f);
+            }
             xn[k] = v;
-            xs[k * npix + i] = v;
+            if (v != xv[k] || v != v) xs[k * npix + i] = v;
         }
         if (partial) {
             float ph = 0.0f;
+            if (use_bar) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                ph += xn[k] > 0.0f ? -logf(xn[k]) : INFINITY;
-                if (!lower_only) ph += xn[k] < 1.0f ? -logf(1.0f - xn[k]) : INFINITY;
+                for (int k = 0; k < K; ++k) {
+                    ph += xn[k] > 0.0f ? -logf(xn[k]) : INFINITY;
+                    if (!prm.lower_only) ph += xn[k] < 1.0f ? -logf(1.0f - xn[k]) : INFINITY;
+                }
             }
             float rg = 0.0f;
-            if (K == 2 && reg_w != 0.0f) rg = reg_w * fabsf(xn[0] * xn[1]);
-            pen += (double)(beta * rg + bt * ph);
+            if (use_reg) rg = prm.reg_w * fabsf(xn[0] * xn[1]);
+            pen += (double)(prm.beta_reg * rg) + (use_bar ? (double)(bt * ph) : 0.0);
         }
     }
     if (partial) {

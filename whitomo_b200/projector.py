@@ -116,8 +116,8 @@ class Projector(object):
         _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, _ptr(ws), nbytes, _stream()))
         return out.reshape(lead + self.sino_shape)
 
-    def bp(self, sino, out=None, angle_range=None):
-        """g = W^T q (exact transpose).  sino (..., nangles, ndet) -> (..., rows, cols)."""
+    def bp(self, sino, out=None, angle_range=None, scale=1.0):
+        """g = scale * W^T q (exact transpose).  sino (..., nangles, ndet) -> (..., rows, cols)."""
         s, lead = self._as_images(sino, self.sino_shape)
         n = s.shape[0]
         if out is None:
@@ -125,7 +125,8 @@ class Projector(object):
         a0, a1 = (0, self.nangles) if angle_range is None else angle_range
         nbytes = self.lib.wt_workspace_bytes(self.handle, n)
         ws = self._workspace(nbytes)
-        _capi.check(self.lib.wt_bp(self.handle, _ptr(s), _ptr(out), n, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
+        _capi.check(self.lib.wt_bp(self.handle, _ptr(s), _ptr(out), n, int(a0), int(a1), float(scale), _ptr(ws), nbytes,
+                                   _stream()))
         return out.reshape(lead + self.vol_shape)
 
     def sirt(self, sino, n_iters=100):
@@ -151,7 +152,7 @@ class Projector(object):
 
     def fbp(self, sino):
         """x = pi/(2A) * W^T ramp(p)  (cpu_fbp, src/astra_proxy.py:87-102)."""
-        return self.bp(self.ramp_filter(sino)) * (np.pi / (2.0 * self.nangles))
+        return self.bp(self.ramp_filter(sino), scale=np.pi / (2.0 * self.nangles))
 
     def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True):
         """Fused white-beam forward model + residual (wt_white_fp).  conc (S, K, rows, cols) or (K, rows, cols).
@@ -175,11 +176,14 @@ class Projector(object):
                                          _ptr(loss), S, _ptr(ws), nbytes, _stream()))
         return inten, qmu, loss
 
-    def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, lower_only=False, want_penalty=False):
-        """In-place fused box-barrier gradient step (wt_barrier_update).  x, grad: (S, K, rows, cols)."""
+    def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, triv_w=0.0, lower_only=False,
+                       mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None, want_penalty=False):
+        """In-place fused K3 step (wt_barrier_update).  x, grad: (S, K, rows, cols) / (K, rows, cols) / (rows, cols)."""
         if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
             raise ValueError("x must be a contiguous float32 tensor on %s" % self.device)
-        g = grad if (grad.dtype == torch.float32 and grad.is_contiguous()) else grad.float().contiguous()
+        g = grad
+        if g is not None and not (g.dtype == torch.float32 and g.is_contiguous()):
+            g = g.float().contiguous()
         if x.dim() == 2:
             S, K = 1, 1
         elif x.dim() == 3:
@@ -187,10 +191,15 @@ class Projector(object):
         else:
             S, K = x.shape[0], x.shape[1]
         npix = x.shape[-1] * x.shape[-2]
+        prm = _capi.UpdateParams(float(alpha), float(beta_reg), float(t), float(reg_w), float(triv_w),
+                                 int(bool(lower_only)), int(mode), int(elem_mask) & 0xFFFFFFFF)
+        act = None
+        if active is not None:
+            act = active.to(torch.uint8).contiguous()
+            assert act.numel() == S
         pen = torch.empty((S,), dtype=torch.float64, device=self.device) if want_penalty else None
-        nbytes = self.lib.wt_workspace_bytes(self.handle, S * K)
+        nbytes = max(int(self.lib.wt_workspace_bytes(self.handle, S * K)), S * 296 * 8)
         ws = self._workspace(nbytes)
-        _capi.check(self.lib.wt_barrier_update(_ptr(x), _ptr(g), S, K, npix, float(alpha), float(beta_reg), float(t),
-                                               float(reg_w), int(bool(lower_only)), _ptr(pen), _ptr(ws), nbytes,
-                                               _stream()))
+        _capi.check(self.lib.wt_barrier_update(_ptr(x), _ptr(g), S, K, npix, ctypes.byref(prm), _ptr(act), _ptr(pen),
+                                               _ptr(ws), nbytes, _stream()))
         return pen

@@ -1,0 +1,116 @@
+"""Device-resident solver loops for the reference's concrete scenarios.  Everything between the input upload and
+the result download stays in HBM; each inner iteration is K1 (fused epilogue) -> K2 -> K3, i.e. K FP + K BP
+(white-beam) or 1-2 FP + 1 BP (mono) where the reference spends 3K FP + K BP / >= 4 FP + 2 BP on the same
+arithmetic.
+
+  white_barrier_stack     src/barrier_method_gogo.py:79-94,179-193 driven by src/barrier_method.py:155-240,
+                          goal = WhiteProjection.func/grad, over a stack of independent slices
+  white_rec_stack         src/white_rec.py:199-244,338-368 (plain gradient descent `Iteration`)
+  barrier_least_squares   teeth_recon/experiments.py:651-749 (mono metal-artifact reduction, HoughBarrier)
+  sirt                    src/astra_proxy.py:69-84 / teeth_recon/experiments.py:352-356
+
+Slices of a stack are independent problems sharing one geometry; the early-stop rule of barrier_method
+(src/barrier_method.py:208-229) is therefore applied per slice through an `active` mask.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _as_stack(x, K):
+    """(K,N,N) or (S,K,N,N) -> (S,K,N,N) float32 contiguous clone"""
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    assert x.dim() == 4 and x.shape[1] == K
+    return x.to(torch.float32).contiguous().clone()
+
+
+def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1, t_step=0.5, alpha=1.0,
+                        beta_reg=1.0, ir_beta=0.05, max_iter=5000, do_alpha_decay=True, min_delta_loss=1e-3,
+                        n_steps_without_progress=15, stat_cb=None, max_total_iters=None):
+    """Log-barrier reconstruction of element concentrations 0 <= c <= 1 with the 0.05*|c0 c1| regulariser.
+
+    Defaults are the reference's run (src/barrier_method_gogo.py:184-192).  ``meas`` (S, A, D) intensities,
+    ``x0`` (S, K, N, N) feasible start.  Returns (x, info) with info = dict(iters, loss (S,), trace list).
+    Per inner iteration and slice: one fused white-beam FP (K projections), K BP, one K3 launch.
+    The loss of barrier_method's early-stop test at the new point is f(x') + penalty(x'); f(x') is the by-product
+    of the FP that the next iteration's gradient needs anyway, so no projection is spent on statistics.
+    """
+    K = spectrum.K
+    x = _as_stack(x0, K)
+    S = x.shape[0]
+    meas = meas.reshape((S,) + proj.sino_shape).to(torch.float32).contiguous()
+    dev = x.device
+    if not bool(((x > 0) & (x < 1)).all()):         # src/barrier_method.py:128-152 (box projection, then re-check)
+        x.clamp_(0, 1)
+        if not bool(((x >= 0) & (x <= 1)).all()):
+            return x, None
+    t = float(t0)
+    total = 0
+    trace = []
+    _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
+    for i_biter in range(n_biter):
+        prev = None
+        stall = torch.zeros(S, dtype=torch.int32, device=dev)
+        active = torch.ones(S, dtype=torch.bool, device=dev)
+        for i_iter in range(n_iter):
+            g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+            if stat_cb is not None:
+                stat_cb(dict(biter=i_biter, iter=i_iter, t=t, alpha=alpha, x=x, func=f_loss, grad=g))
+            pen = proj.barrier_update(x, g, alpha, beta_reg, t, reg_w=ir_beta, active=active,
+                                      want_penalty=n_steps_without_progress is not None)
+            _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
+            total += 1
+            if n_steps_without_progress is not None:
+                loss = f_loss + pen
+                if prev is not None:
+                    progress = (prev - loss) >= min_delta_loss       # False for nan/inf, like the reference
+                    stall = torch.where(active, torch.where(progress, torch.zeros_like(stall), stall + 1), stall)
+                prev = loss if prev is None else torch.where(active, loss, prev)
+                active = active & (stall < n_steps_without_progress)
+                trace.append(loss.detach())
+                if not bool(active.any()):
+                    break
+            if max_total_iters is not None and total >= max_total_iters:
+                break
+        t *= t_step
+        if do_alpha_decay:
+            alpha = alpha * math.sqrt(t_step)
+            n_iter = min(int(n_iter / t_step), max_iter)
+        if max_total_iters is not None and total >= max_total_iters:
+            break
+    return x, dict(iters=total, loss=f_loss, trace=trace)
+
+
+def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=1e-2, clip_concentrations=True,
+                    dissimilarity_constraint=True, triv_conc_constraint=True, alternate=True):
+    """Plain gradient descent of src/white_rec.py:199-244,338-368 (flags as at :342-345, alpha/beta at :42-43):
+    step = alpha*(grad + beta*(d|c0 c1| + c(c(4c-3)+1))); iteration i updates element 0 when i % 4 == 0 else
+    element 1... (the reference zeroes step[1] when i % 4 == 0 and step[0] otherwise, :229-233); clip to [0, 1].
+    Returns (c, losses) with losses[i] = ||q_i|| + ||beta c0 c1|| per slice (:236-237)."""
+    K = spectrum.K
+    c = _as_stack(c0, K)
+    S = c.shape[0]
+    meas = meas.reshape((S,) + proj.sino_shape).to(torch.float32).contiguous()
+    losses = []
+    mode = _capi.UPD_STEP_CLIP if clip_concentrations else _capi.UPD_STEP_ONLY
+    for it in range(n_iters):
+        _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
+        g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+        reg_loss = 0.0
+        if dissimilarity_constraint and K == 2:
+            reg_loss = torch.linalg.vector_norm((beta_reg * c[:, 0] * c[:, 1]).reshape(S, -1), dim=1).double()
+        losses.append(torch.sqrt(2.0 * f_loss) + reg_loss)
+        mask = 0xFFFFFFFF
+        if alternate and K == 2:
+            mask = 0b01 if it % 4 == 0 else 0b10
+        proj.barrier_update(c, g, alpha, beta_reg, 0.0, reg_w=1.0 if (dissimilarity_constraint and K == 2) else 0.0,
+                            triv_w=1.0 if triv_conc_constraint else 0.0, mode=mode, elem_mask=mask)
+    return c, losses
+
+
+def sirt(proj, sino, n_iters=100):
+    return proj.sirt(sino, n_iters)
