@@ -39,11 +39,13 @@ struct Carver {
     bool ok() const { return off <= cap; }
 };
 
+static size_t vn_floats(const wt_geom *g, int n) { return (size_t)n * g->rows * fp_pitch(g->cols); }
+static size_t vt_floats(const wt_geom *g, int n) { return (size_t)n * g->cols * fp_pitch(g->rows); }
 static size_t packed_vol_floats(const wt_geom *g, int n) {
-    return align_up((size_t)n * g->rows * (g->cols + 2 * VPAD), 64) + align_up((size_t)n * g->cols * (g->rows + 2 * VPAD), 64);
+    return align_up(vn_floats(g, n), 64) + align_up(vt_floats(g, n), 64);
 }
 static size_t packed_sino_floats(const wt_geom *g, int n) { return align_up((size_t)n * g->nangles * g->sino_pitch, 64); }
-static int fp_blocks(const wt_geom *g) { return ((g->ndet + FP_DT - 1) / FP_DT) * ((g->nangles + FP_AT - 1) / FP_AT); }
+static int fp_blocks(const wt_geom *g) { return ((g->ndet + FP_DT - 1) / FP_DT) * g->ntiles; }
 
 // images are processed in chunks of V in {4,2,1} interleaved images
 struct Chunk { int v, first, groups; };
@@ -59,11 +61,13 @@ static std::vector<Chunk> chunks(int n, int multiple_of = 1) {
 }
 
 template <int V, class Epi>
-static void fp_chunk(const FpParams &p, const Epi &epi, const float *src, float *vn, float *vt, int groups, cudaStream_t st) {
+static cudaError_t fp_chunk(const FpParams &p, const Epi &epi, const float *src, float *vn, float *vt, int groups,
+                            cudaStream_t st) {
     if constexpr (V % Epi::kMult == 0) {
         launch_pack_vol<V>(src, vn, vt, p.R, p.C, groups, st);
-        launch_fp<V>(p, epi, groups, st);
+        return launch_fp<V>(p, epi, groups, st);
     }
+    return cudaSuccess;
 }
 
 template <class Epi>
@@ -73,14 +77,15 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     for (const Chunk &c : chunks(n, multiple_of)) {
         FpParams p;
         p.vn = vn; p.vt = vt; p.ang = g->d_fp;
+        p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
         p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
         p.a_begin = a_begin; p.a_end = a_end;
         const float *src = vol + (size_t)c.first * img;
         Epi epi = epi_proto.offset(c.first);
         switch (c.v) {
-        case 4: fp_chunk<4>(p, epi, src, vn, vt, c.groups, st); break;
-        case 2: fp_chunk<2>(p, epi, src, vn, vt, c.groups, st); break;
-        default: fp_chunk<1>(p, epi, src, vn, vt, c.groups, st); break;
+        case 4: WT_CUDA(fp_chunk<4>(p, epi, src, vn, vt, c.groups, st)); break;
+        case 2: WT_CUDA(fp_chunk<2>(p, epi, src, vn, vt, c.groups, st)); break;
+        default: WT_CUDA(fp_chunk<1>(p, epi, src, vn, vt, c.groups, st)); break;
         }
         WT_CUDA(cudaGetLastError());
     }
@@ -204,6 +209,34 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
         b.a1 = (float)((double)f.len - (double)f.len * fabs(f.c0_step));
         b.pad_ = 0.0f;
     }
+    // angle tiles of the forward projector: consecutive angles of one orientation whose rays, over any
+    // FP_DT-detector x FP_LB-line patch, stay within FP_WFIT positions of each other.  c_a - c_b is affine in
+    // (d, l), so the spread across angles is convex and peaks at a corner of the (d, l) rectangle.
+    std::vector<FpTile> tiles;
+    {
+        auto c_at = [&](int a, int d, int l) { return fp[a].c0_base + ((double)d + 0.5) * fp[a].c0_step + (double)l * fp[a].delta; };
+        int a = 0;
+        while (a < nangles) {
+            int cnt = 1;
+            while (cnt < FP_AT && a + cnt < nangles && fp[a + cnt].vertical == fp[a].vertical) {
+                const int n = cnt + 1;
+                const int nl = fp[a].vertical ? rows : cols;
+                double worst = 0.0, ms = 0.0, md = 0.0;
+                for (int i = 0; i < n; ++i) { ms = fmax(ms, fabs(fp[a + i].c0_step)); md = fmax(md, fabs((double)fp[a + i].delta)); }
+                const int dc[2] = {0, ndet - 1}, lc[2] = {0, nl - 1};
+                for (int di = 0; di < 2; ++di)
+                    for (int li = 0; li < 2; ++li) {
+                        double lo = 1e300, hi = -1e300;
+                        for (int i = 0; i < n; ++i) { const double c = c_at(a + i, dc[di], lc[li]); lo = fmin(lo, c); hi = fmax(hi, c); }
+                        worst = fmax(worst, hi - lo);
+                    }
+                if (worst + (FP_DT - 1) * ms + (FP_LB - 1) * md > (double)FP_WFIT) break;
+                cnt = n;
+            }
+            tiles.push_back({a, cnt});
+            a += cnt;
+        }
+    }
     wt_geom *g = new wt_geom();
     g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
     // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row
@@ -213,13 +246,16 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
     g->sino_pitch = (padl + ndet + padl + BP_SEGW + 3) & ~3;
-    g->d_fp = nullptr; g->d_bp = nullptr;
+    g->d_fp = nullptr; g->d_bp = nullptr; g->d_tiles = nullptr;
+    g->ntiles = (int)tiles.size();
     g->h_angles = (float *)malloc(sizeof(float) * nangles);
     memcpy(g->h_angles, angles, sizeof(float) * nangles);
     cudaError_t e = cudaMalloc(&g->d_fp, sizeof(FpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_bp, sizeof(BpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_fp, fp.data(), sizeof(FpAngle) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_bp, bp.data(), sizeof(BpAngle) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_tiles, sizeof(FpTile) * tiles.size());
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_tiles, tiles.data(), sizeof(FpTile) * tiles.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         wt_geom_destroy(g);
         return cuda_fail(e, "wt_geom_create");
@@ -232,6 +268,7 @@ void wt_geom_destroy(wt_geom *g) {
     if (!g) return;
     if (g->d_fp) cudaFree(g->d_fp);
     if (g->d_bp) cudaFree(g->d_bp);
+    if (g->d_tiles) cudaFree(g->d_tiles);
     free(g->h_angles);
     delete g;
 }
@@ -258,8 +295,8 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws
     if (nimages <= 0) return invalid("wt_fp: nimages must be positive");
     if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     Carver cv(ws, ws_bytes);
-    float *vn = cv.take<float>((size_t)nimages * g->rows * (g->cols + 2 * VPAD));
-    float *vt = cv.take<float>((size_t)nimages * g->cols * (g->rows + 2 * VPAD));
+    float *vn = cv.take<float>(vn_floats(g, nimages));
+    float *vt = cv.take<float>(vt_floats(g, nimages));
     HFpStore epi;
     epi.sino = sino;
     epi.plane = (size_t)g->nangles * g->ndet;
@@ -295,8 +332,8 @@ int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)g->nangles * g->ndet, img = (size_t)g->rows * g->cols;
     Carver cv(ws, ws_bytes);
-    float *vn = cv.take<float>((size_t)nimages * g->rows * (g->cols + 2 * VPAD));
-    float *vt = cv.take<float>((size_t)nimages * g->cols * (g->rows + 2 * VPAD));
+    float *vn = cv.take<float>(vn_floats(g, nimages));
+    float *vt = cv.take<float>(vt_floats(g, nimages));
     float *sp = cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
     float *raysum = cv.take<float>(plane);
     float *pixsum = cv.take<float>(img);
@@ -354,8 +391,8 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)g->nangles * g->ndet;
     Carver cv(ws, ws_bytes);
-    float *vn = cv.take<float>((size_t)n * g->rows * (g->cols + 2 * VPAD));
-    float *vt = cv.take<float>((size_t)n * g->cols * (g->rows + 2 * VPAD));
+    float *vn = cv.take<float>(vn_floats(g, n));
+    float *vt = cv.take<float>(vt_floats(g, n));
     float *sp = cv.take<float>((size_t)n * g->nangles * g->sino_pitch);  // generic-K path: holds P (n, A, D)
     float *partial = cv.take<float>((size_t)n * fp_blocks(g));
     int nb = 0;
@@ -401,15 +438,21 @@ int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, 
         partial = (double *)ws;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int bx = (int)((npix + 255) / 256);
+    const bool vec = (npix % 4 == 0) && (((uintptr_t)x | (uintptr_t)grad) % 16 == 0);
+    const size_t work = vec ? npix / 4 : npix;
+    int bx = (int)((work + 255) / 256);
     if (bx > UPD_BLOCKS_PER_SLICE) bx = UPD_BLOCKS_PER_SLICE;
     dim3 grid(bx, nslices);
+#define WT_UPD_LAUNCH(KK)                                                                                     \
+    if (vec) barrier_update_kernel<KK, 4><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial);         \
+    else barrier_update_kernel<KK, 1><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial)
     switch (n_elements) {
-    case 1: barrier_update_kernel<1><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
-    case 2: barrier_update_kernel<2><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
-    case 3: barrier_update_kernel<3><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
-    default: barrier_update_kernel<4><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial); break;
+    case 1: WT_UPD_LAUNCH(1); break;
+    case 2: WT_UPD_LAUNCH(2); break;
+    case 3: WT_UPD_LAUNCH(3); break;
+    default: WT_UPD_LAUNCH(4); break;
     }
+#undef WT_UPD_LAUNCH
     WT_CUDA(cudaGetLastError());
     if (penalty) {
         reduce_partials_f64_kernel<<<nslices, 32, 0, st>>>(partial, bx, 1.0, penalty);

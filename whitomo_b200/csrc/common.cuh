@@ -57,6 +57,8 @@ struct wt_geom {
     int sino_pitch;  // packed sinogram row pitch in detector positions (multiple of 4)
     wt::FpAngle *d_fp;
     wt::BpAngle *d_bp;
+    void *d_tiles;   // wt::FpTile[ntiles]: angle tiles of the forward projector
+    int ntiles;
     float *h_angles;
 };
 

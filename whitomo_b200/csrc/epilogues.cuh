@@ -170,68 +170,111 @@ __global__ void reduce_partials_f64_kernel(const double *__restrict__ partial, i
 // One thread per pixel handles all K elements of one slice (K <= 4).  HBM-bound: reads x, g; writes x.
 constexpr int UPD_BLOCKS_PER_SLICE = 296;  // 2 CTAs per SM worth of partials per slice
 
+struct UpdFlags {
+    bool act, clip, use_reg, use_bar, lower_only, want_pen;
+    float bt;
+};
+
+// one pixel, all K elements: returns the penalty contribution of the new point
 template <int K>
+__device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const UpdFlags &f, const float (&xv)[K],
+                                           const float (&gv)[K], float (&xn)[K]) {
+    float sgn = 0.0f;
+    if (f.use_reg) {
+        const float pr = xv[0] * xv[1];
+        sgn = pr > 0.0f ? 1.0f : (pr < 0.0f ? -1.0f : 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float v = xv[k];
+        if (f.act && ((prm.elem_mask >> k) & 1u)) {
+            float gt = gv[k];
+            float rg = 0.0f;
+            if (f.use_reg) rg = prm.reg_w * (xv[K == 2 ? 1 - k : 0] * sgn);
+            if (prm.triv_w != 0.0f) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
+            gt += prm.beta_reg * rg;
+            if (f.use_bar) {
+                gt += f.bt * (-1.0f / v);
+                if (!f.lower_only) gt += f.bt * (1.0f / (1.0f - v));
+            }
+            v = v - prm.alpha * gt;
+        }
+        if (f.clip) {
+            v = fmaxf(v, 0.0f);
+            if (!f.lower_only) v = fminf(v, 1.0f);
+        }
+        xn[k] = v;
+    }
+    float pen = 0.0f;
+    if (f.want_pen) {
+        if (f.use_bar) {
+            float ph = 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                // -log(x) - log(1-x) = -log(x (1-x)); +inf on (or outside) the boundary like phi[f >= 0] = inf
+                const float arg = f.lower_only ? xn[k] : xn[k] * (1.0f - xn[k]);
+                const bool inside = f.lower_only ? (xn[k] > 0.0f) : (xn[k] > 0.0f && xn[k] < 1.0f);
+                ph += inside ? -logf(arg) : INFINITY;
+            }
+            pen = f.bt * ph;
+        }
+        if (f.use_reg) pen += prm.beta_reg * (prm.reg_w * fabsf(xn[0] * xn[1]));
+    }
+    return pen;
+}
+
+// VEC = 4: every thread owns 4 consecutive pixels (16-byte loads/stores), VEC = 1: scalar fallback for
+// pixel counts that are not a multiple of 4.  grid = (blocks per slice, slices).
+template <int K, int VEC>
 __global__ void __launch_bounds__(256) barrier_update_kernel(float *__restrict__ x, const float *__restrict__ grad,
                                                              size_t npix, wt_update_params prm,
                                                              const unsigned char *__restrict__ active, double *partial) {
+    typedef typename VecOf<VEC>::T VecT;
     const size_t slice = blockIdx.y;
     float *xs = x + slice * K * npix;
     const float *gs = grad ? grad + slice * K * npix : nullptr;
-    const bool act = (!active || active[slice]) && prm.mode != WT_UPD_CLIP_ONLY;
-    const bool clip = prm.mode != WT_UPD_STEP_ONLY && (!active || active[slice]);
-    const bool use_reg = (K == 2) && prm.reg_w != 0.0f;
-    const bool use_bar = prm.t != 0.0f;
-    const float bt = prm.beta_reg * prm.t;
-    double pen = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-        float xv[K], xn[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) xv[k] = xs[k * npix + i];
-        float sgn = 0.0f;
-        if (use_reg) {
-            const float pr = xv[0] * xv[1];
-            sgn = pr > 0.0f ? 1.0f : (pr < 0.0f ? -1.0f : 0.0f);
-        }
+    UpdFlags f;
+    const bool sl_on = !active || active[slice];
+    f.act = sl_on && prm.mode != WT_UPD_CLIP_ONLY;
+    f.clip = sl_on && prm.mode != WT_UPD_STEP_ONLY;
+    f.use_reg = (K == 2) && prm.reg_w != 0.0f;
+    f.use_bar = prm.t != 0.0f;
+    f.lower_only = prm.lower_only != 0;
+    f.want_pen = partial != nullptr;
+    f.bt = prm.beta_reg * prm.t;
+    const bool writes = f.act || f.clip;
+    float pen = 0.0f;
+    const size_t nvec = npix / VEC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        float xv[K][VEC], gv[K][VEC], xo[K][VEC];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float v = xv[k];
-            if (act && ((prm.elem_mask >> k) & 1u)) {
-                float gt = __ldg(gs + k * npix + i);
-                float rg = 0.0f;
-                if (use_reg) rg = prm.reg_w * (xv[K == 2 ? 1 - k : 0] * sgn);
-                if (prm.triv_w != 0.0f) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
-                gt += prm.beta_reg * rg;
-                if (use_bar) {
-                    gt += bt * (-1.0f / v);
-                    if (!prm.lower_only) gt += bt * (1.0f / (1.0f - v));
-                }
-                v = v - prm.alpha * gt;
-            }
-            if (clip) {
-                v = fmaxf(v, 0.0f);
-                if (!prm.lower_only) v = fminf(v, 1.0f);
-            }
-            xn[k] = v;
-            if (v != xv[k] || v != v) xs[k * npix + i] = v;
-        }
-        if (partial) {
-            float ph = 0.0f;
-            if (use_bar) {
+            unpack<VEC>(reinterpret_cast<const VecT *>(xs + k * npix)[i], xv[k]);
+            if (f.act) {
+                unpack<VEC>(__ldg(reinterpret_cast<const VecT *>(gs + k * npix) + i), gv[k]);
+            } else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    ph += xn[k] > 0.0f ? -logf(xn[k]) : INFINITY;
-                    if (!prm.lower_only) ph += xn[k] < 1.0f ? -logf(1.0f - xn[k]) : INFINITY;
-                }
+                for (int j = 0; j < VEC; ++j) gv[k][j] = 0.0f;
             }
-            float rg = 0.0f;
-            if (use_reg) rg = prm.reg_w * fabsf(xn[0] * xn[1]);
-            pen += (double)(prm.beta_reg * rg) + (use_bar ? (double)(bt * ph) : 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float a[K], g[K], o[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { a[k] = xv[k][j]; g[k] = gv[k][j]; }
+            pen += upd_pixel<K>(prm, f, a, g, o);
+#pragma unroll
+            for (int k = 0; k < K; ++k) xo[k][j] = o[k];
+        }
+        if (writes) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) reinterpret_cast<VecT *>(xs + k * npix)[i] = pack<VEC>(xo[k]);
         }
     }
     if (partial) {
         __shared__ double red[8];
-        pen = warp_sum(pen);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pen;
+        double pd = warp_sum((double)pen);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pd;
         __syncthreads();
         if (threadIdx.x == 0) {
             double s = 0.0;

@@ -1,20 +1,44 @@
 // K1: ray-driven Joseph forward projector (ASTRA 'linear' projector semantics),
-// V images interleaved per position so that one 4V-byte load feeds V updates.
+// V images interleaved per position so that one 16-byte shared-memory load feeds V updates.
 //
-// Work decomposition: thread <-> ray (angle a, detector d); a warp holds 32 adjacent detectors of one
-// angle, a CTA FP_DT detectors x FP_AT consecutive angles (consecutive angles walk almost the same
-// pixels, so their warps share L1 lines).  "vertical" angles march over rows of the row-major packed
-// volume, "horizontal" angles over rows of the transposed packed copy -- both are the same loop, and
-// adjacent lanes always read adjacent positions of one line (coalesced).
+// Work decomposition.  Thread <-> ray (angle a, detector d).  A CTA owns FP_DT detectors x FP_AT angles
+// of one "angle tile" (consecutive angles of the same orientation whose rays stay within one window,
+// grouped on the host at geometry creation) and marches over the lines of the volume in chunks of
+// FP_LB lines.  For every chunk one warp asks the TMA unit (cp.async.bulk, one 1-D bulk copy per line)
+// to stage the FP_W-position window of those lines that the tile's rays cross; completion is tracked
+// with one mbarrier per stage, FP_STAGES deep, so the copies of later chunks overlap the gathers of the
+// current one.  "Vertical" angles read the row-major packed volume, "horizontal" angles the transposed
+// packed copy -- the same loop either way.
+//
+// Lane mapping.  A quarter-warp (the unit the LSU serves per shared-memory wavefront for 16-byte loads)
+// holds 4 adjacent detectors x 2 adjacent angles: their two Joseph taps fall within < 8 consecutive
+// 16-byte positions, i.e. distinct banks or the same word -> conflict-free LDS.128 at the full
+// 128 B/clk/SM.  (The first version of this kernel gathered through L1 with __ldg: a warp's 32 adjacent
+// detectors span 5-7 cache lines per load and ncu showed l1tex at 98% with 2.3x the minimum wavefronts;
+// see profiles/r1_ncu_full_v1_summary.txt.)
 #pragma once
 #include "common.cuh"
 
 namespace wt {
 
-constexpr int FP_DT = 64;  // detectors per CTA
-constexpr int FP_AT = 4;   // angles per CTA
+constexpr int FP_DT = 32;       // detectors per CTA
+constexpr int FP_AT = 8;        // angles per CTA (one angle tile)
+constexpr int FP_THREADS = FP_DT * FP_AT;
+constexpr int FP_LB = 16;       // lines per staged chunk
+constexpr int FP_W = 96;        // positions per staged line window
+constexpr int FP_STAGES = 4;
+// budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
+// for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
+constexpr int FP_WFIT = FP_W - 8;
 
-// ---- packing: plain (n, R, C) -> VN (G, R, C+2*VPAD, V) and VT (G, C, R+2*VPAD, V), zero padded -------
+__host__ __device__ inline int fp_pitch(int npos) {
+    int p = npos + 2 * VPAD;
+    if (p < FP_W) p = FP_W;
+    return (p + 3) & ~3;
+}
+
+// ---- packing: plain (n, R, C) -> VN (G, R, pitch(C), V) and VT (G, C, pitch(R), V), zero padded -------
+// position k of a line lives at slot k + VPAD; everything else in the line is zero.
 template <int V>
 __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__ vol, float *__restrict__ vn,
                                                        float *__restrict__ vt, int R, int C) {
@@ -23,7 +47,7 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
     const int g = blockIdx.z;
     const int r0 = blockIdx.y * 32 - VPAD, c0 = blockIdx.x * 32 - VPAD;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int Cp = C + 2 * VPAD, Rp = R + 2 * VPAD;
+    const int Cp = fp_pitch(C), Rp = fp_pitch(R);
     const size_t img = (size_t)R * C;
     const float *src = vol + (size_t)g * V * img;
 #pragma unroll
@@ -56,15 +80,23 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
 
 template <int V>
 inline void launch_pack_vol(const float *vol, float *vn, float *vt, int R, int C, int groups, cudaStream_t st) {
-    dim3 grid((C + 2 * VPAD + 31) / 32, (R + 2 * VPAD + 31) / 32, groups);
+    // the tile grid covers the padded extents of both copies (pitch may exceed npos + 2*VPAD for tiny volumes)
+    const int ext_c = max(fp_pitch(C), C + 2 * VPAD), ext_r = max(fp_pitch(R), R + 2 * VPAD);
+    dim3 grid((ext_c + 31) / 32, (ext_r + 31) / 32, groups);
     pack_vol_kernel<V><<<grid, dim3(32, 8), 0, st>>>(vol, vn, vt, R, C);
 }
 
 // ---- projector ------------------------------------------------------------------------------------
+struct FpTile {
+    int first, count;  // angles [first, first + count), count <= FP_AT, all of one orientation
+};
+
 struct FpParams {
     const float *vn;
     const float *vt;
     const FpAngle *ang;
+    const FpTile *tiles;
+    int ntiles;
     int R, C, D, A;
     int a_begin, a_end;
 };
@@ -83,74 +115,180 @@ struct FpEpiStore {
 };
 
 template <int V>
-__device__ __forceinline__ void fp_ray(const FpParams &p, const FpAngle &an, int g, int d, float (&val)[V]) {
+struct FpSmem {
     typedef typename VecOf<V>::T VecT;
-    const int nlines = an.vertical ? p.R : p.C;
-    const int npos = an.vertical ? p.C : p.R;
-    const int pitch = npos + 2 * VPAD;
-    const VecT *base = reinterpret_cast<const VecT *>(an.vertical ? p.vn : p.vt) + (size_t)g * nlines * pitch + VPAD;
-    const float c0 = (float)(an.c0_base + ((double)d + 0.5) * an.c0_step);
-    const float delta = an.delta;
+    VecT seg[FP_STAGES][FP_LB][FP_W];
+    uint64_t full[FP_STAGES];
+    float wstart[FP_STAGES];
+    float cmin[FP_AT], cmax[FP_AT], delta[FP_AT];  // per angle of the tile: position range at line 0, slope
+    int lo, hi;                                    // line range any ray of the CTA needs
+};
 
-    // lines on which floor(c) can be inside [-1, npos-1]; the estimate may be off by one line on each
-    // side, which the zero padding absorbs (|delta| <= 1, VPAD = 4).
-    int l_lo, l_hi;
-    if (fabsf(delta) * (float)nlines < 0.5f) {
-        const bool hit = (c0 > -2.0f) && (c0 < (float)npos + 1.0f);
-        l_lo = 0;
-        l_hi = hit ? nlines : 0;
-    } else {
-        const float inv = 1.0f / delta;
-        const float t0 = (-1.0f - c0) * inv, t1 = ((float)npos - c0) * inv;
-        const float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
-        l_lo = (int)fmaxf(floorf(lo), 0.0f);
-        l_hi = (int)fminf(ceilf(hi) + 1.0f, (float)nlines);
+template <int V, class Epi>
+__global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
+    typedef typename VecOf<V>::T VecT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FpSmem<V> &sm = *reinterpret_cast<FpSmem<V> *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp = 16 detectors x 2 angles; quarter-warp = 4 detectors x 2 angles
+    const int slot = (warp >> 1) * 2 + (lane & 1);
+    const int d0 = blockIdx.x * FP_DT;
+    const int d = d0 + (warp & 1) * 16 + (lane >> 3) * 4 + ((lane >> 1) & 3);
+    const FpTile tile = p.tiles[blockIdx.y];
+    const int a = tile.first + slot;
+    const int g = blockIdx.z;
+    const bool valid = (slot < tile.count) && (d < p.D) && (a >= p.a_begin) && (a < p.a_end);
+
+    // orientation is uniform over the tile
+    const FpAngle an0 = p.ang[tile.first];
+    const int nlines = an0.vertical ? p.R : p.C;
+    const int npos = an0.vertical ? p.C : p.R;
+    const int pitch = fp_pitch(npos);
+    const VecT *base = reinterpret_cast<const VecT *>(an0.vertical ? p.vn : p.vt) + (size_t)g * nlines * pitch;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < FP_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        mbar_fence_init();
+        sm.lo = nlines;
+        sm.hi = 0;
     }
+    if (tid < FP_AT) {
+        // position range of the tile's rays of this angle at line 0 (detectors d0 .. min(d0+DT, D)-1)
+        float lo_c = 3.0e38f, hi_c = -3.0e38f, dl = 0.0f;
+        const int aa = tile.first + tid;
+        if (tid < tile.count && aa >= p.a_begin && aa < p.a_end) {
+            const FpAngle an = p.ang[aa];
+            const int dl_ = min(d0 + FP_DT, p.D) - 1;
+            const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
+            const double cb = an.c0_base + ((double)dl_ + 0.5) * an.c0_step;
+            lo_c = (float)fmin(ca, cb);
+            hi_c = (float)fmax(ca, cb);
+            dl = an.delta;
+        }
+        sm.cmin[tid] = lo_c;
+        sm.cmax[tid] = hi_c;
+        sm.delta[tid] = dl;
+    }
+    __syncthreads();
+
+    float c0h = 0.0f, delta = 0.0f, len = 0.0f;
+    int l_lo = 0, l_hi = 0;
+    if (valid) {
+        const FpAngle an = p.ang[a];
+        const float c0 = (float)(an.c0_base + ((double)d + 0.5) * an.c0_step);
+        delta = an.delta;
+        len = an.len;
+        c0h = c0 - 0.5f;
+        // lines on which floor(c) can be inside [-1, npos-1]; the estimate may be off by one line on each side,
+        // which the zero padding absorbs (|delta| <= 1, VPAD = 4)
+        if (fabsf(delta) * (float)nlines < 0.5f) {
+            const bool hit = (c0 > -2.0f) && (c0 < (float)npos + 1.0f);
+            l_lo = 0;
+            l_hi = hit ? nlines : 0;
+        } else {
+            const float inv = 1.0f / delta;
+            const float t0 = (-1.0f - c0) * inv, t1 = ((float)npos - c0) * inv;
+            l_lo = (int)fmaxf(floorf(fminf(t0, t1)), 0.0f);
+            l_hi = (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)nlines);
+        }
+        if (l_hi > l_lo) {
+            atomicMin(&sm.lo, l_lo);
+            atomicMax(&sm.hi, l_hi);
+        }
+    }
+    __syncthreads();
+    const int Lb = sm.lo, Le = sm.hi;
+    const int nchunk = Le > Lb ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
+
+    // producer (warp 0): stage chunk `ch` = lines [Lb + ch*LB, +LB)
+    auto produce = [&](int ch) {
+        const int s = ch % FP_STAGES;
+        const int l0 = Lb + ch * FP_LB;
+        const int l1 = min(l0 + FP_LB, nlines) - 1;
+        // left-most position any ray of the tile takes on these lines (linear in l: attained at an end)
+        float m = 3.0e38f;
+        if (lane < FP_AT) {
+            const float cm = sm.cmin[lane], dl = sm.delta[lane];
+            if (cm < 1.0e38f) m = fminf(fmaf((float)l0, dl, cm), fmaf((float)l1, dl, cm));
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        m = __shfl_sync(0xffffffffu, m, 0);
+        int ws = (int)floorf(m) - 2;
+        ws = max(ws, -VPAD);
+        ws = min(ws, pitch - VPAD - FP_W);
+        ws = (ws + VPAD) & ~(4 / V - 1);            // slot index (>= 0), 16-byte aligned
+        const int nl = l1 - l0 + 1;
+        if (lane == 0) {
+            sm.wstart[s] = (float)(ws - VPAD);       // position of window slot 0
+            mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nl * FP_W * sizeof(VecT)));
+        }
+        __syncwarp();
+        if (lane < nl)
+            tma_load_1d(&sm.seg[s][lane][0], base + (size_t)(l0 + lane) * pitch + ws, (uint32_t)(FP_W * sizeof(VecT)),
+                        &sm.full[s]);
+    };
+
+    if (warp == 0)
+        for (int b = 0; b < FP_STAGES - 1 && b < nchunk; ++b) produce(b);
 
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+    constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer
+    constexpr int MAGIC_BITS = 0x4B400000;
 
-    const VecT *line = base + (size_t)l_lo * pitch;
-    float lf = (float)l_lo;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int s = ch % FP_STAGES;
+        if (warp == 0 && ch + FP_STAGES - 1 < nchunk) {
+            fence_proxy_async();
+            produce(ch + FP_STAGES - 1);
+        }
+        mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
+        const int l0 = Lb + ch * FP_LB;
+        const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
+        if (la < lb) {
+            // c - 0.5 relative to the window start at line la; then one FADD per line
+            float cr = fmaf((float)la, delta, c0h) - sm.wstart[s];
+            const VecT *row = &sm.seg[s][la - l0][0];
 #pragma unroll 4
-    for (int l = l_lo; l < l_hi; ++l) {
-        const float c = fmaf(lf, delta, c0);
-        const float fl = floorf(c);
-        const float off = c - fl;
-        const int col = (int)fl;
-        float v0[V], v1[V];
-        unpack<V>(__ldg(line + col), v0);
-        unpack<V>(__ldg(line + col + 1), v1);
+            for (int l = la; l < lb; ++l) {
+                const float t = cr + MAGIC;                 // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
+                const float off = (cr - (t - MAGIC)) + 0.5f;
+                const int idx = __float_as_int(t) - MAGIC_BITS;
+                float v0[V], v1[V];
+                unpack<V>(row[idx], v0);
+                unpack<V>(row[idx + 1], v1);
+                const float w0 = 1.0f - off;
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] += fmaf(off, v1[i] - v0[i], v0[i]);
-        line += pitch;
-        lf += 1.0f;
+                for (int i = 0; i < V; ++i) acc[i] = fmaf(off, v1[i], fmaf(w0, v0[i], acc[i]));
+                cr += delta;
+                row += FP_W;
+            }
+        }
+        __syncthreads();  // everyone is done with stage s before it is refilled
     }
-#pragma unroll
-    for (int i = 0; i < V; ++i) val[i] = acc[i] * an.len;
-}
 
-template <int V, class Epi>
-__global__ void __launch_bounds__(FP_DT *FP_AT) fp_kernel(FpParams p, Epi epi) {
-    const int d = blockIdx.x * FP_DT + threadIdx.x;
-    const int a = p.a_begin + blockIdx.y * FP_AT + threadIdx.y;
-    const int g = blockIdx.z;
-    const bool valid = (d < p.D) && (a < p.a_end);
     float val[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) val[i] = 0.0f;
-    if (valid) {
-        const FpAngle an = p.ang[a];
-        fp_ray<V>(p, an, g, d, val);
-    }
+    for (int i = 0; i < V; ++i) val[i] = acc[i] * len;
     epi.template operator()<V>(p, g, a, d, valid, val);
 }
 
 template <int V, class Epi>
-inline void launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
-    dim3 grid((p.D + FP_DT - 1) / FP_DT, (p.a_end - p.a_begin + FP_AT - 1) / FP_AT, groups);
-    fp_kernel<V, Epi><<<grid, dim3(FP_DT, FP_AT), 0, st>>>(p, epi);
+inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
+    const size_t smem = sizeof(FpSmem<V>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((p.D + FP_DT - 1) / FP_DT, p.ntiles, groups);
+    fp_kernel<V, Epi><<<grid, FP_THREADS, smem, st>>>(p, epi);
+    return cudaSuccess;
 }
 
 }  // namespace wt
