@@ -50,9 +50,10 @@ int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles
 size_t wt_workspace_bytes(const wt_geom *g, int nimages);
 
 /* p = W x.  Replaces gpu_fp (src/astra_proxy.py:35-49: ASTRA 'FP' with the 'linear' projector).
- * vol (nimages, rows, cols) -> sino (nimages, nangles, ndet). */
-int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws, size_t ws_bytes,
-          void *stream);
+ * vol (nimages, rows, cols) -> sino (nimages, nangles, ndet).  Only sinogram rows [angle_begin, angle_end) are
+ * computed and written (the angle-range split of one oversized slice); pass 0, nangles for the full operator. */
+int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angle_begin, int angle_end,
+          void *ws, size_t ws_bytes, void *stream);
 
 /* g = scale * W^T q (exact transpose).  Replaces gpu_bp (src/astra_proxy.py:52-66: ASTRA 'BP'); scale = 1 is
  * the plain operator, -1 gives the white-beam gradient sign (src/white_projection.py:112), pi/(2A) the FBP
@@ -82,10 +83,25 @@ void wt_spectrum_destroy(wt_spectrum *s);
  *   mu_k[r] = -pix sum_e s_e w_e ea[k,e] exp(...);  qmu_k = q * mu_k;  loss = 1/2 sum_r q^2.
  * conc (nslices, K, rows, cols); meas (nslices, nangles, ndet) or NULL (then q = -I);
  * outputs, each optional (NULL to skip): intensity (nslices, nangles, ndet), qmu (nslices, K, nangles, ndet),
- * loss (nslices) as float64. */
+ * loss (nslices) as float64.  Only rays of angles [angle_begin, angle_end) are computed, written and summed into
+ * the loss (angle-range split: the model is local to a ray, the partial losses of the ranks add up). */
 int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const float *meas,
-                float *intensity, float *qmu, double *loss, int nslices, void *ws, size_t ws_bytes,
-                void *stream);
+                float *intensity, float *qmu, double *loss, int nslices, int angle_begin, int angle_end,
+                void *ws, size_t ws_bytes, void *stream);
+
+/* Mono metal-artifact-reduction residual, fused into the projector epilogue.  Replaces, per inner iteration of
+ * barrier_least_squares (teeth_recon/experiments.py:651-749), the FP inside cost/grad (:712-722) and the FP inside
+ * HoughBarrier.eval (teeth_recon/barrier.py:50-69).  With P = W x, per image i and ray r:
+ *   good ray  (mask == 0):  u = 2 (P - b) * inv_ngood[i]                (the reference's grad = 2 BP(d / n_good), B8)
+ *   metal ray (mask != 0):  u = -bt / (P - b_hb)                        (beta*t * grad phi of  b_hb - P <= 0)
+ * so that ONE backprojection W^T u is  grad cost + beta*t*grad phi_hough.  stats (nimages, 3) float64, optional:
+ *   [0] cost = sum_good ((P - b) inv_ngood)^2,  [1] sum_metal -log(P - b_hb) (+inf if infeasible),
+ *   [2] number of infeasible metal rays (P < b_hb).
+ * vol (nimages, rows, cols); b (nimages, nangles, ndet); mask (nimages, nangles, ndet) bytes; inv_ngood (nimages);
+ * u (nimages, nangles, ndet), optional; proj (nimages, nangles, ndet), optional plain projections. */
+int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned char *mask,
+              const float *inv_ngood, float bt, float b_hb, float *u, float *proj, double *stats, int nimages,
+              void *ws, size_t ws_bytes, void *stream);
 
 /* K3: fused gradient-combine + regularisers + log-barrier + step + projection, one streaming pass.
  * Replaces, per inner iteration,

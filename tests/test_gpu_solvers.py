@@ -1,0 +1,196 @@
+"""Parity of the host-side mirrors and the fused device solver loops against the oracle / the goldens produced by
+the reference's own Python modules.  Needs a B200: -m gpu.  Tolerance on reconstructions: rel. L2 <= 1e-3."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import white as ow, barrier as ob
+from conftest import rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+TOL_OP, TOL_REC = 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_astra_proxy_numpy_api(golden):
+    """the reference's call forms: gpu_fp/gpu_bp/cpu_sirt/cpu_fbp with numpy in/out, and the verbatim ASTRA object
+    manager sequence of src/astra_proxy.py:35-49 through the shim"""
+    from whitomo_b200 import astra_proxy as ap
+    astra = ap.astra
+    n, na = 64, 48
+    pg = astra.create_proj_geom('parallel', 1.0, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    vg = astra.create_vol_geom(n, n)
+    pid = astra.create_projector('linear', pg, vg)
+    g = oracle.Geometry.standard(n, na)
+    x = np.random.default_rng(0).random((n, n))            # float64 in, like the reference
+    p = ap.gpu_fp(pg, vg, x, pid)
+    assert isinstance(p, np.ndarray) and p.dtype == np.float32 and p.shape == (na, g.ndet)
+    assert rel_l2(p, oracle.fp(g, x)) < TOL_OP
+    v = ap.gpu_bp(pg, vg, p, pid, supersampling=3)
+    assert v.dtype == np.float32 and rel_l2(v, oracle.bp(g, p)) < TOL_OP
+    assert rel_l2(ap.cpu_sirt(pg, vg, pid, p, n_iters=20), oracle.sirt(g, p, 20)) < TOL_REC
+    assert rel_l2(ap.cpu_fbp(pg, vg, pid, p, n_iters=7), oracle.fbp(g, p)) < TOL_REC
+    with pytest.raises(ValueError):
+        ap.gpu_fp(pg, vg, np.zeros((n, n + 1)), pid)
+    # object-manager form (teeth_recon/experiments.py:103-192 carries this copy of astra_proxy)
+    apx = ap.AstraProxy(2)
+    v_id = apx.data_create('-vol', vg, x)
+    rt_id = apx.data_create('-sino', pg)
+    cfg = astra.astra_dict(apx.fp_algo_name)
+    cfg['VolumeDataId'], cfg['ProjectionDataId'], cfg['ProjectorId'] = v_id, rt_id, pid
+    alg = astra.algorithm.create(cfg)
+    astra.algorithm.run(alg)
+    assert np.array_equal(apx.data_get(rt_id), p)
+    astra.algorithm.delete(alg)
+    apx.data_delete(rt_id)
+    apx.data_delete(v_id)
+    # CUDA tensors pass straight through
+    pt = ap.gpu_fp(pg, vg, torch.from_numpy(x.astype(np.float32)).cuda(), pid)
+    assert pt.is_cuda and np.array_equal(pt.cpu().numpy(), p)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_white_projection_class_vs_reference_module(golden, tag):
+    from whitomo_b200.white_projection import WhiteProjection
+    z = golden("white_small")
+    n, na = int(z[tag + "_n"]), int(z[tag + "_n_angles"])
+    wp = WhiteProjection(source=z[tag + "_source"], pixel_size=float(z[tag + "_pixel_size"]),
+                         element_numbers=np.array([301, 302]), element_absorptions=z[tag + "_ea"],
+                         energy_grid=z[tag + "_grid"], ph_size=(n, n), n_angles=na)      # sinogram=None works (B1)
+    assert wp.proj_shape == (na, int(np.sqrt(2) * n + 1)) and wp.conc_shape == (2, n, n)
+    wp.calc_sinogram_with_gt(z[tag + "_gt"])
+    assert rel_l2(wp.sinogram, z[tag + "_sinogram"]) < TOL_OP
+    c = z[tag + "_c"]
+    f = wp.func(c)
+    assert abs(f - float(z[tag + "_func"])) < 1e-4 * float(z[tag + "_func"])
+    g = wp.grad(c)
+    assert g.dtype == np.float64 and g.shape == c.shape and rel_l2(g, z[tag + "_grad"]) < 5e-4
+    I, exp_arg, exp, flat_fp = wp.FP_white(c)
+    assert I.shape == (wp.proj_shape[0] * wp.proj_shape[1],) and flat_fp.shape == (2, I.shape[0], 1)
+    assert rel_l2(I, z[tag + "_I"]) < TOL_OP and rel_l2(wp.calc_mu(exp), z[tag + "_mu"]) < TOL_OP
+    conc, mu = wp.BP_white(wp.sinogram - I, exp)
+    assert rel_l2(conc, z[tag + "_grad"]) < 5e-4
+    assert rel_l2(wp.FP(c[0]), oracle.fp(oracle.Geometry.standard(n, na), c[0])) < TOL_OP
+
+
+def test_generic_barrier_method_on_device_tensors(golden, capsys):
+    """the array-agnostic driver with CUDA-tensor closures over the engine reproduces the reference golden"""
+    from whitomo_b200 import barrier_method as bm, white_rec
+    from whitomo_b200.white_projection import WhiteProjection
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    wp = WhiteProjection(z["source"], float(z["pixel_size"]), np.array([301, 302]), z["ea"], z["grid"], (n, n), n_angles=na)
+    wp.calc_sinogram_with_gt(z["gt"])
+    ir = float(z["ir_beta"])
+    dev = lambda a: torch.from_numpy(np.asarray(a, np.float32)).cuda()
+    goal = (lambda x: wp.func_grad_dev(x)[0].item(), lambda x: wp.grad_dev(x))
+    reg = (lambda x: ir * torch.abs(x[0] * x[1]), lambda x: ir * white_rec.calc_uneq_reg_grad(x))
+    nonneg = (lambda x: -x, lambda x: -torch.ones_like(x), lambda x: torch.clamp(x, min=0))
+    le_one = (lambda x: x - 1, lambda x: torch.ones_like(x), lambda x: torch.clamp(x, max=1))
+    p = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+    ans, _ = bm.barrier_method(dev(z["x0"]), goal, reg_dict={"r": reg}, ineq_dict={"a": nonneg, "b": le_one}, **p)
+    assert rel_l2(ans.cpu().numpy(), z["ans"]) < TOL_REC
+
+
+def test_white_barrier_stack_vs_reference_golden(golden):
+    """fused device loop (K FP + K BP per iteration) == the reference's barrier_method run, slice by slice"""
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    grid = z["grid"]
+    P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    sp = Spectrum(z["source"] / np.sum(z["source"] * grid[:, 1]), grid[:, 1], z["ea"], float(z["pixel_size"]))
+    gt = torch.from_numpy(z["gt"].astype(np.float32)).cuda()
+    meas, _, _ = P.white_fp(sp, gt, want_qmu=False, want_loss=False)
+    p = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+    # a 3-slice stack: slice 0 and 2 are the golden problem, slice 1 a different start
+    x0 = np.stack([z["x0"], 0.5 * z["x0"] + 0.2, z["x0"]]).astype(np.float32)
+    x, info = solvers.white_barrier_stack(P, sp, meas.expand(3, -1, -1).contiguous(), torch.from_numpy(x0).cuda(),
+                                          ir_beta=float(z["ir_beta"]), **p)
+    assert rel_l2(x[0].cpu().numpy(), z["ans"]) < TOL_REC
+    assert torch.equal(x[0], x[2]) and not torch.equal(x[0], x[1])
+    assert info["iters"] > 0 and torch.isfinite(info["loss"]).all()
+
+
+def test_white_rec_stack_vs_oracle_iteration(golden):
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    z = golden("white_small")
+    n, na = int(z["a_n"]), int(z["a_n_angles"])
+    grid = z["a_grid"]
+    wo = ow.WhiteOracle(z["a_source"], float(z["a_pixel_size"]), z["a_ea"], grid, (n, n), n_angles=na)
+    wo.calc_sinogram_with_gt(z["a_gt"])
+    P = Projector(n, n, wo.geom.ndet, np.linspace(0, np.pi, na))
+    sp = Spectrum(wo.source, grid[:, 1], z["a_ea"], float(z["a_pixel_size"]))
+    meas = torch.from_numpy(wo.sinogram.reshape(wo.proj_shape).astype(np.float32)).cuda()
+    c = z["a_c"].copy()
+    alpha, beta = 0.7, 1e-2                                                   # src/white_rec.py:42-43
+    ref_losses = []
+    for it in range(9):
+        c, fl = ow.iteration(wo, c, alpha, beta, clip_concentrations=True, dissimilarity_constraint=True,
+                             triv_conc_constraint=True, iter_num=it)
+        ref_losses.append(fl)
+    cd, losses = solvers.white_rec_stack(P, sp, meas[None], torch.from_numpy(z["a_c"].astype(np.float32)).cuda(),
+                                         n_iters=9, alpha=alpha, beta_reg=beta)
+    assert rel_l2(cd[0].cpu().numpy(), c) < TOL_REC
+    assert np.allclose([l.item() for l in losses], ref_losses, rtol=1e-3)
+
+
+def test_mar_barrier_least_squares_vs_reference_golden(golden):
+    from whitomo_b200.projector import Projector
+    from whitomo_b200 import solvers
+    z = golden("barrier_mar")
+    n, na = int(z["n"]), int(z["n_angles"])
+    P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    nb = int(z["n_biter"])
+    x = solvers.barrier_least_squares(P, z["projections"].copy(), float(z["i0"]), float(z["bound"]), n_biter=nb)
+    assert x is not None and rel_l2(x.cpu().numpy(), z["ans"]) < 5e-3
+    x2 = solvers.barrier_least_squares(P, z["projections"].copy(), float(z["i0"]), float(z["bound"]), n_iter=100,
+                                       n_biter=nb, t0=0.1, max_iter=1000, do_alpha_decay=True, with_sino_barrier=False)
+    assert rel_l2(x2.cpu().numpy(), z["ans_no_ineq"]) < 5e-3
+
+
+def test_hough_barrier_class_on_device_closures(golden):
+    from whitomo_b200.projector import Projector
+    from whitomo_b200.barrier import HoughBarrier
+    n, na = 32, 24
+    g = oracle.Geometry.standard(n, na)
+    P = Projector(n, n, g.ndet, np.linspace(0, np.pi, na))
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.2, 1.0, n * n).astype(np.float32)
+    FPn = lambda v: oracle.fp(g, v.reshape(n, n)).flatten()
+    m = (rng.random(na * g.ndet) < 0.1) & (FPn(x) > 5.0)          # constrained rays well inside the object
+    BPn = lambda v: oracle.bp(g, v.reshape(g.sino_shape)).flatten()
+    FPd = lambda v: P.fp(v.reshape(n, n)).flatten()
+    BPd = lambda v: P.bp(v.reshape(g.sino_shape)).flatten()
+    b = 0.5 * float(FPn(x)[m].min())
+    hn = ob.HoughBarrier(FPn, BPn, m, b, np.zeros(g.sino_shape, np.float32))
+    hd = HoughBarrier(FPd, BPd, torch.from_numpy(m).cuda(), b, torch.zeros(g.sino_shape, device="cuda"))
+    pn, gn = hn.eval(x)
+    pd, gd = hd.eval(torch.from_numpy(x).cuda())
+    assert rel_l2(pd.cpu().numpy(), pn) < TOL_OP and rel_l2(gd.cpu().numpy(), gn) < TOL_OP
+    assert hd.is_feasible(torch.from_numpy(x).cuda())
+    x_bad = 0.01 * x
+    assert not hd.is_feasible(torch.from_numpy(x_bad).cuda())
+    assert rel_l2(hd.project(torch.from_numpy(x_bad).cuda()).cpu().numpy(), hn.project(x_bad)) < TOL_REC
+
+
+def test_fp_angle_range_and_angle_split_single_rank():
+    from whitomo_b200.projector import Projector
+    from whitomo_b200.distributed import AngleSplit
+    P = Projector(48, 48, 69, np.linspace(0, np.pi, 40))
+    x = torch.rand(2, 48, 48, device="cuda")
+    full = P.fp(x)
+    part = P.fp(x, angle_range=(11, 29))
+    assert torch.equal(part[:, 11:29], full[:, 11:29]) and part[:, :11].abs().sum() == 0 and part[:, 29:].abs().sum() == 0
+    sp = AngleSplit(P)
+    assert sp.range == (0, 40) and torch.equal(sp.fp(x), full)
+    y = torch.rand(40, 69, device="cuda")
+    assert torch.equal(sp.bp(y), P.bp(y))

@@ -17,14 +17,16 @@ SIGNATURES = {
     "wt_geom_destroy": (None, [c_void_p]),
     "wt_geom_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "wt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
-    "wt_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "wt_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "wt_mar_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                          c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "wt_bp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "wt_sirt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "wt_sirt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "wt_spectrum_create": (c_int, [c_int, c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_double),
                                    ctypes.POINTER(c_double), c_double, ctypes.POINTER(c_void_p)]),
     "wt_spectrum_destroy": (None, [c_void_p]),
-    "wt_white_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+    "wt_white_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
     "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),

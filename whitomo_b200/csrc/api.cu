@@ -135,6 +135,19 @@ struct HBpSirt : BpEpiSirtUpdate {
     size_t img;
     HBpSirt offset(int first) const { HBpSirt e = *this; e.vol = vol + (size_t)first * img; return e; }
 };
+struct HFpMar : FpEpiMar {
+    static constexpr int kMult = 1;
+    size_t plane;
+    int nblocks;
+    HFpMar offset(int first) const {
+        HFpMar e = *this;
+        e.b = b + (size_t)first * plane; e.mask = mask + (size_t)first * plane; e.inv_ngood = inv_ngood + first;
+        if (e.u) e.u += (size_t)first * plane;
+        if (e.proj) e.proj += (size_t)first * plane;
+        if (e.partial) e.partial += (size_t)first * nblocks;
+        return e;
+    }
+};
 template <int K>
 struct HFpWhite : FpEpiWhite<K> {
     static constexpr int kMult = K;
@@ -285,14 +298,16 @@ int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles
 size_t wt_workspace_bytes(const wt_geom *g, int nimages) {
     if (!g || nimages <= 0) return 0;
     size_t fl = packed_vol_floats(g, nimages) + packed_sino_floats(g, nimages);
-    fl += align_up((size_t)nimages * fp_blocks(g), 64);                      // loss partials (float)
+    fl += align_up((size_t)3 * nimages * fp_blocks(g), 64);                  // per-CTA partials (float)
     size_t bytes = fl * sizeof(float) + align_up((size_t)nimages * UPD_BLOCKS_PER_SLICE * sizeof(double), 256);
     return bytes + 4096;
 }
 
-int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws, size_t ws_bytes, void *stream) {
+int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angle_begin, int angle_end, void *ws,
+          size_t ws_bytes, void *stream) {
     if (!g || !vol || !sino || !ws) return invalid("wt_fp: null pointer");
     if (nimages <= 0) return invalid("wt_fp: nimages must be positive");
+    if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_fp: bad angle range");
     if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     Carver cv(ws, ws_bytes);
     float *vn = cv.take<float>(vn_floats(g, nimages));
@@ -300,7 +315,36 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, void *ws
     HFpStore epi;
     epi.sino = sino;
     epi.plane = (size_t)g->nangles * g->ndet;
-    return run_fp(g, vol, nimages, 0, g->nangles, vn, vt, epi, (cudaStream_t)stream);
+    return run_fp(g, vol, nimages, angle_begin, angle_end, vn, vt, epi, (cudaStream_t)stream);
+}
+
+int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned char *mask, const float *inv_ngood,
+              float bt, float b_hb, float *u, float *proj, double *stats, int nimages, void *ws, size_t ws_bytes,
+              void *stream) {
+    if (!g || !vol || !b || !mask || !inv_ngood || !ws) return invalid("wt_mar_fp: null pointer");
+    if (nimages <= 0) return invalid("wt_mar_fp: nimages must be positive");
+    if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_mar_fp: workspace too small"; return WT_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws, ws_bytes);
+    float *vn = cv.take<float>(vn_floats(g, nimages));
+    float *vt = cv.take<float>(vt_floats(g, nimages));
+    cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
+    const int nb = fp_blocks(g);
+    float *partial = cv.take<float>((size_t)3 * nimages * nb);
+    HFpMar e;
+    e.b = b; e.mask = mask; e.inv_ngood = inv_ngood; e.bt = bt; e.b_hb = b_hb; e.u = u; e.proj = proj;
+    e.partial = stats ? partial : nullptr; e.nimg = nimages;
+    e.plane = (size_t)g->nangles * g->ndet; e.nblocks = nb;
+    int rc = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, e, st);
+    if (rc) return rc;
+    if (stats) {
+        // stats is (nimages, 3): reduce each of the three planes with stride 3
+        for (int q = 0; q < 3; ++q) {
+            reduce_partials_strided_kernel<<<nimages, 32, 0, st>>>(partial + (size_t)q * nimages * nb, nb, stats + q, 3);
+            WT_CUDA(cudaGetLastError());
+        }
+    }
+    return WT_OK;
 }
 
 int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, float scale,
@@ -383,9 +427,11 @@ void wt_spectrum_destroy(wt_spectrum *s) {
 }
 
 int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const float *meas, float *intensity,
-                float *qmu, double *loss, int nslices, void *ws, size_t ws_bytes, void *stream) {
+                float *qmu, double *loss, int nslices, int angle_begin, int angle_end, void *ws, size_t ws_bytes,
+                void *stream) {
     if (!g || !s || !conc || !ws) return invalid("wt_white_fp: null pointer");
     if (nslices <= 0) return invalid("wt_white_fp: nslices must be positive");
+    if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_white_fp: bad angle range");
     const int K = s->K, n = nslices * K;
     if (ws_bytes < wt_workspace_bytes(g, n)) { g_err = "wt_white_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -402,20 +448,21 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
         if (K == 1) {
             HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
             e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
-            rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, e, st, 1);
+            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st, 1);
         } else {
             HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
             e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
-            rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, e, st, 2);
+            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st, 2);
         }
         if (rc) return rc;
     } else {
         HFpStore fs; fs.sino = sp; fs.plane = plane;
-        int rc = run_fp(g, conc, n, 0, g->nangles, vn, vt, fs, st);
+        int rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, fs, st);
         if (rc) return rc;
         nb = (int)((plane + 255) / 256);
         white_epilogue_kernel<<<dim3(nb, nslices), 256, 0, st>>>(sp, s->d_tab, K, s->E, meas, intensity, qmu,
-                                                                  loss ? partial : nullptr, plane);
+                                                                  loss ? partial : nullptr, plane,
+                                                                  (size_t)angle_begin * g->ndet, (size_t)angle_end * g->ndet);
         WT_CUDA(cudaGetLastError());
     }
     if (loss) {

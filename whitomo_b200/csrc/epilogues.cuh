@@ -61,10 +61,10 @@ struct FpEpiWhite {
                                                const float (&val)[V]) const {
         static_assert(V % K == 0, "group must hold whole slices");
         constexpr int SPG = V / K;
-        __shared__ float red[SPG][FP_DT * FP_AT / 32];
+        __shared__ float red[SPG][FP_THREADS / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        const int tid = threadIdx.x;
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
@@ -100,8 +100,64 @@ struct FpEpiWhite {
             if (tid < SPG) {
                 float s = 0.0f;
 #pragma unroll
-                for (int w = 0; w < FP_DT * FP_AT / 32; ++w) s += red[tid][w];
+                for (int w = 0; w < FP_THREADS / 32; ++w) s += red[tid][w];
                 partial[((size_t)g * SPG + tid) * nblocks + bid] = s;
+            }
+        }
+    }
+};
+
+// ---- mono MAR residual fused into the projector (teeth_recon/experiments.py:712-722, teeth_recon/barrier.py:50-69)
+struct FpEpiMar {
+    const float *b;              // (n, A, D)
+    const unsigned char *mask;   // (n, A, D)
+    const float *inv_ngood;      // (n)
+    float bt, b_hb;
+    float *u;                    // (n, A, D) or null
+    float *proj;                 // (n, A, D) or null
+    float *partial;              // (3, n, nblocks) or null
+    int nimg;                    // n of this launch (stride of the partial planes)
+    template <int V>
+    __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
+                                               const float (&val)[V]) const {
+        __shared__ float red[3][V][FP_THREADS / 32];
+        const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
+        const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const int tid = threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const size_t im = (size_t)g * V + i;
+            float cost = 0.0f, phi = 0.0f, bad = 0.0f;
+            if (valid) {
+                const size_t o = im * plane + r;
+                const float P = val[i];
+                float uu;
+                if (mask[o]) {
+                    const float fx = P - b_hb;                      // = -(b_hb - P)
+                    uu = bt != 0.0f ? -bt / fx : 0.0f;
+                    phi = fx > 0.0f ? -logf(fx) : INFINITY;
+                    bad = P < b_hb ? 1.0f : 0.0f;
+                } else {
+                    const float dd = (P - __ldg(b + o)) * __ldg(inv_ngood + im);
+                    uu = 2.0f * dd;
+                    cost = dd * dd;
+                }
+                if (u) u[o] = uu;
+                if (proj) proj[o] = P;
+            }
+            if (partial) {
+                cost = warp_sum(cost); phi = warp_sum(phi); bad = warp_sum(bad);
+                if ((tid & 31) == 0) { red[0][i][tid >> 5] = cost; red[1][i][tid >> 5] = phi; red[2][i][tid >> 5] = bad; }
+            }
+        }
+        if (partial) {
+            __syncthreads();
+            if (tid < 3 * V) {
+                const int q = tid / V, i = tid % V;
+                float s = 0.0f;
+#pragma unroll
+                for (int w = 0; w < FP_THREADS / 32; ++w) s += red[q][i][w];
+                partial[((size_t)q * nimg + (size_t)g * V + i) * nblocks + bid] = s;
             }
         }
     }
@@ -110,11 +166,11 @@ struct FpEpiWhite {
 // generic-K path: P (S, K, A, D) already projected; one thread per ray
 __global__ void white_epilogue_kernel(const float *__restrict__ P, const float *__restrict__ tab, int K, int E,
                                       const float *__restrict__ meas, float *inten, float *qmu, float *partial,
-                                      size_t plane) {
+                                      size_t plane, size_t r_begin, size_t r_end) {
     const size_t slice = blockIdx.y;
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     float q2 = 0.0f;
-    if (r < plane) {
+    if (r >= r_begin && r < r_end) {
         float I = 0.0f;
         for (int e = 0; e < E; ++e) {
             float arg = 0.0f;
@@ -157,6 +213,13 @@ __global__ void reduce_partials_kernel(const float *__restrict__ partial, int nb
     for (int b = threadIdx.x; b < nb; b += 32) acc += (double)partial[(size_t)s * nb + b];
     acc = warp_sum(acc);
     if (threadIdx.x == 0) out[s] = scale * acc;
+}
+__global__ void reduce_partials_strided_kernel(const float *__restrict__ partial, int nb, double *out, int stride) {
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) acc += (double)partial[(size_t)s * nb + b];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[(size_t)s * stride] = acc;
 }
 __global__ void reduce_partials_f64_kernel(const double *__restrict__ partial, int nb, double scale, double *out) {
     const int s = blockIdx.x;

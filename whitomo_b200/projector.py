@@ -105,15 +105,18 @@ class Projector(object):
         return t.reshape((-1,) + tuple(shape)).contiguous(), lead
 
     # ---- operators ------------------------------------------------------------------------------
-    def fp(self, vol, out=None):
-        """p = W x.  vol (..., rows, cols) -> (..., nangles, ndet) float32 on the device."""
+    def fp(self, vol, out=None, angle_range=None):
+        """p = W x.  vol (..., rows, cols) -> (..., nangles, ndet) float32 on the device.  With angle_range only
+        those sinogram rows are computed (the others are zero in a fresh output)."""
         v, lead = self._as_images(vol, self.vol_shape)
         n = v.shape[0]
+        a0, a1 = (0, self.nangles) if angle_range is None else angle_range
         if out is None:
-            out = torch.empty((n,) + self.sino_shape, dtype=torch.float32, device=self.device)
+            alloc = torch.empty if angle_range is None else torch.zeros
+            out = alloc((n,) + self.sino_shape, dtype=torch.float32, device=self.device)
         nbytes = self.lib.wt_workspace_bytes(self.handle, n)
         ws = self._workspace(nbytes)
-        _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, _ptr(ws), nbytes, _stream()))
+        _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
         return out.reshape(lead + self.sino_shape)
 
     def bp(self, sino, out=None, angle_range=None, scale=1.0):
@@ -154,7 +157,8 @@ class Projector(object):
         """x = pi/(2A) * W^T ramp(p)  (cpu_fbp, src/astra_proxy.py:87-102)."""
         return self.bp(self.ramp_filter(sino), scale=np.pi / (2.0 * self.nangles))
 
-    def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True):
+    def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True,
+                 angle_range=None):
         """Fused white-beam forward model + residual (wt_white_fp).  conc (S, K, rows, cols) or (K, rows, cols).
         Returns (intensity (S,A,D) | None, qmu (S,K,A,D) | None, loss (S,) float64 | None)."""
         c, lead = self._as_images(conc, self.vol_shape)
@@ -167,14 +171,33 @@ class Projector(object):
             m, _ = self._as_images(meas, self.sino_shape)
             if m.shape[0] != S:
                 raise ValueError("meas must hold one sinogram per slice")
-        inten = torch.empty((S,) + self.sino_shape, dtype=torch.float32, device=self.device) if want_intensity else None
-        qmu = torch.empty((S, K) + self.sino_shape, dtype=torch.float32, device=self.device) if want_qmu else None
+        a0, a1 = (0, self.nangles) if angle_range is None else angle_range
+        alloc = torch.empty if angle_range is None else torch.zeros
+        inten = alloc((S,) + self.sino_shape, dtype=torch.float32, device=self.device) if want_intensity else None
+        qmu = alloc((S, K) + self.sino_shape, dtype=torch.float32, device=self.device) if want_qmu else None
         loss = torch.empty((S,), dtype=torch.float64, device=self.device) if want_loss else None
         nbytes = self.lib.wt_workspace_bytes(self.handle, S * K)
         ws = self._workspace(nbytes)
         _capi.check(self.lib.wt_white_fp(self.handle, spectrum.handle, _ptr(c), _ptr(m), _ptr(inten), _ptr(qmu),
-                                         _ptr(loss), S, _ptr(ws), nbytes, _stream()))
+                                         _ptr(loss), S, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
         return inten, qmu, loss
+
+    def mar_fp(self, vol, b, mask, inv_ngood, bt, b_hb, want_u=True, want_proj=False, want_stats=True):
+        """Fused mono-MAR residual (wt_mar_fp).  vol (n, R, C); b (n, A, D); mask (n, A, D) uint8; inv_ngood (n,).
+        Returns (u | None, proj | None, stats (n, 3) float64 | None): cost, hough phi sum, #infeasible metal rays."""
+        v, _ = self._as_images(vol, self.vol_shape)
+        n = v.shape[0]
+        bb, _ = self._as_images(b, self.sino_shape)
+        mm = mask.to(self.device, dtype=torch.uint8).reshape((n,) + self.sino_shape).contiguous()
+        ig = inv_ngood.to(self.device, dtype=torch.float32).reshape(n).contiguous()
+        u = torch.empty((n,) + self.sino_shape, dtype=torch.float32, device=self.device) if want_u else None
+        pr = torch.empty((n,) + self.sino_shape, dtype=torch.float32, device=self.device) if want_proj else None
+        st = torch.empty((n, 3), dtype=torch.float64, device=self.device) if want_stats else None
+        nbytes = self.lib.wt_workspace_bytes(self.handle, n)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_mar_fp(self.handle, _ptr(v), _ptr(bb), _ptr(mm), _ptr(ig), float(bt), float(b_hb),
+                                       _ptr(u), _ptr(pr), _ptr(st), n, _ptr(ws), nbytes, _stream()))
+        return u, pr, st
 
     def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, triv_w=0.0, lower_only=False,
                        mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None, want_penalty=False):

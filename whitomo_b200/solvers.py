@@ -114,3 +114,90 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
 
 def sirt(proj, sino, n_iters=100):
     return proj.sirt(sino, n_iters)
+
+
+def ray_transform_from_projection(p, bound, i0):
+    """teeth_recon/experiments.py:290-293: m = p <= bound; p[m] = bound; r = log i0 - log p (p is modified, like
+    the reference).  Torch tensors or numpy arrays."""
+    m = p <= bound
+    p[m] = bound
+    if isinstance(p, torch.Tensor):
+        return math.log(i0) - torch.log(p), m
+    return np.log(i0) - np.log(p), m
+
+
+def _bc_project(proj, x, m, b_hb, n_iter=100, alpha=1e-2):
+    """HoughBarrier's projection onto {FP(x)[m] >= b} (teeth_recon/barrier.py:30-45, B11 kept literally)."""
+    f = proj.fp(x)
+    x_new = x.clone()
+    for _ in range(n_iter):
+        infeas = m & (f < b_hb)
+        if not bool(infeas.any()):
+            break
+        f = torch.where(infeas, f - (b_hb + 1e-3), torch.zeros_like(f))
+        x_new = x_new - alpha * proj.bp(f)
+        f = proj.fp(x_new)
+    return x_new
+
+
+def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t_step=0.2, alpha=0.1, beta_reg=1.0,
+                          max_iter=400, do_alpha_decay=False, with_sino_barrier=True, x0_level=1e-2):
+    """Mono metal-artifact reduction of teeth_recon/experiments.py:651-749 on the device (defaults = its first run;
+    the second run is n_iter=100, t0=0.1, max_iter=1000, do_alpha_decay=True, with_sino_barrier=False).
+
+    pr: photon counts (A, D) or (n, A, D).  Per inner iteration: one fused FP (residual on good rays, Hough-barrier
+    term on metal rays, feasibility count), one BP of their sum, one K3 step; the reference spends >= 4 FP + 2 BP
+    (cost-grad FP, HoughBarrier.eval FP, bc_project FP, stats FP; two separate BPs).  The order of the reference
+    is kept: step, then HoughBarrier projection, then clip to x >= 0 (src/barrier_method.py:201-206).
+    Returns x with the leading shape of pr, or (x0, None)-style None if the start cannot be made feasible."""
+    dev = proj.device
+    p = torch.as_tensor(np.asarray(pr) if not isinstance(pr, torch.Tensor) else pr).to(dev, dtype=torch.float32).clone()
+    lead = tuple(p.shape[:-2])
+    p = p.reshape((-1,) + proj.sino_shape)
+    n = p.shape[0]
+    r, m = ray_transform_from_projection(p, bound, i0)
+    bound_log = math.log(i0) - math.log(bound)
+    b = torch.where(m, torch.full_like(r, bound_log), r).contiguous()
+    b_hb = 0.95 * bound_log
+    inv_ngood = 1.0 / (m[0].numel() - m.reshape(n, -1).sum(1)).to(torch.float32)
+    m8 = m.to(torch.uint8).contiguous()
+    if not with_sino_barrier:
+        m_hb = torch.zeros_like(m)
+    else:
+        m_hb = m
+    x = torch.full((n,) + proj.vol_shape, x0_level, dtype=torch.float32, device=dev)
+
+    def fused_fp(t):
+        bt = beta_reg * t if with_sino_barrier else 0.0
+        u, _, st = proj.mar_fp(x, b, m8, inv_ngood, bt, b_hb)
+        return u, st
+
+    # feasibility of the start (src/barrier_method.py:128-152)
+    u, st = fused_fp(t0)
+    if with_sino_barrier and bool((st[:, 2] > 0).any()):
+        x = _bc_project(proj, x, m_hb, b_hb)
+        x.clamp_(min=0)
+        u, st = fused_fp(t0)
+        if bool((st[:, 2] > 0).any()):
+            return None
+    t = float(t0)
+    for _ in range(n_biter):
+        u, st = fused_fp(t)
+        for _ in range(n_iter):
+            g = proj.bp(u)
+            proj.barrier_update(x, g, alpha, beta_reg, t, lower_only=True, mode=_capi.UPD_STEP_ONLY)
+            u, st = fused_fp(t)                     # P at the stepped point: feasibility + next gradient
+            dirty = False
+            if with_sino_barrier and bool((st[:, 2] > 0).any()):
+                x = _bc_project(proj, x, m_hb, b_hb)
+                dirty = True
+            if bool((x < 0).any()):
+                proj.barrier_update(x, None, 0.0, beta_reg, 0.0, lower_only=True, mode=_capi.UPD_CLIP_ONLY)
+                dirty = True
+            if dirty:
+                u, st = fused_fp(t)
+        t *= t_step
+        if do_alpha_decay:
+            alpha = alpha * math.sqrt(t_step)
+            n_iter = min(int(n_iter / t_step), max_iter)
+    return x.reshape(lead + proj.vol_shape)
