@@ -3,10 +3,11 @@
 //   w0 = max(0, A0 - B f),  w1 = max(0, A1 + B f)           (triangle of half-width m, height 1/m).
 //
 // A CTA owns a BP_TW x BP_TH pixel tile and keeps 8 pixels x V images per thread in registers.  For
-// every block of BP_AB angles one warp computes, per angle, where the tile's shadow falls on the
-// detector and asks the TMA unit (cp.async.bulk, one 1-D bulk copy per angle) to stage that
-// BP_SEGW-wide sinogram segment in shared memory; completion is tracked with an mbarrier per stage,
-// BP_STAGES stages deep, so the copies of later angle blocks overlap the gather of the current one.
+// every block of BP_AB angles a dedicated producer warp computes, per angle, where the tile's shadow falls
+// on the detector and asks the TMA unit (cp.async.bulk, one 1-D bulk copy per angle) to stage that
+// BP_SEGW-wide sinogram segment in shared memory.  A full/empty mbarrier pair per stage, BP_STAGES deep,
+// lets the copies of later angle blocks overlap the gather of the current one and lets the 8 consumer
+// warps run without ever synchronising with each other.
 // Lanes run along image columns: their detector positions differ by |cos| <= 1, so the LDS of a warp
 // touches at most 32 consecutive words -- conflict-free.
 #pragma once
@@ -62,13 +63,14 @@ template <int V>
 struct BpSmem {
     typedef typename VecOf<V>::T VecT;
     VecT seg[BP_STAGES][BP_AB][BP_SEGW];
-    float4 cst[BP_STAGES][BP_AB];  // dcol, drow, base, a0
-    float2 cst2[BP_STAGES][BP_AB]; // a1, b
-    uint64_t full[BP_STAGES];
+    float4 cst[BP_STAGES][BP_AB];  // dcol, drow, base - 1/2, Ah = A0 - B/2
+    float2 cst2[BP_STAGES][BP_AB]; // B, unused
+    uint64_t full[BP_STAGES];   // TMA bytes of a stage have landed
+    uint64_t empty[BP_STAGES];  // all consumer warps are done reading a stage
 };
 
 template <int V, class Epi>
-__global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
+__global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BpSmem<V> &sm = *reinterpret_cast<BpSmem<V> *>(smem_raw);
@@ -81,12 +83,15 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < BP_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < BP_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], BP_THREADS / 32);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // producer (warp 0): stage angle block `blk`
+    // producer warp: stage angle block `blk`
     auto produce = [&](int blk) {
         const int s = blk % BP_STAGES;
         const int a = p.a_begin + blk * BP_AB + lane;
@@ -98,18 +103,29 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
             const double dmin = d_t00 + fmin(0.0, (double)(tw - 1) * an.dcol) + fmin(0.0, (double)(th - 1) * an.drow);
             const int lo = (int)floor(dmin) - 1 + p.padl;  // >= 0 by construction of padl
             const int aligned = lo & ~3;
-            sm.cst[s][lane] = make_float4((float)an.dcol, (float)an.drow, (float)(d_t00 + (double)(p.padl - aligned)), an.a0);
-            sm.cst2[s][lane] = make_float2(an.a1, an.b);
+            // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
+            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
+            sm.cst[s][lane] = make_float4((float)an.dcol, (float)an.drow,
+                                          (float)(d_t00 + (double)(p.padl - aligned) - 0.5), an.a0 - 0.5f * an.b);
+            sm.cst2[s][lane] = make_float2(an.b, 0.0f);
             src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
+        if (lane == 0) {
+            fence_proxy_async();  // consumers' generic-proxy reads of this stage precede the refill
+            mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
+        }
         __syncwarp();
         if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
     };
 
-    if (warp == 0) {
-        for (int b = 0; b < BP_STAGES - 1 && b < nblk; ++b) produce(b);
+    if (warp == BP_THREADS / 32) {
+        // runs ahead of the consumers by up to BP_STAGES angle blocks; consumer warps never wait for each other
+        for (int blk = 0; blk < nblk; ++blk) {
+            if (blk >= BP_STAGES) mbar_wait(&sm.empty[blk % BP_STAGES], (uint32_t)(((blk / BP_STAGES) - 1) & 1));
+            produce(blk);
+        }
+        return;
     }
 
     // this thread's pixels: columns lane, lane+32; rows warp, warp+8, warp+16, warp+24 (clamped into the
@@ -120,6 +136,8 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) ir[r] = (float)min(warp + 8 * r, th - 1);
 
+    constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
+    constexpr int MAGIC_BITS = 0x4B400000;
     float acc[4][2][V];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -130,10 +148,6 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int s = blk % BP_STAGES;
-        if (warp == 0 && blk + BP_STAGES - 1 < nblk) {
-            fence_proxy_async();
-            produce(blk + BP_STAGES - 1);
-        }
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
@@ -146,11 +160,11 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const float ds = fmaf(jc[c], c4.x, dr);
-                    const float fl = floorf(ds);
-                    const float f = ds - fl;
-                    const int idx = (int)fl;
-                    const float w0 = fmaxf(0.0f, fmaf(-c2.y, f, c4.w));
-                    const float w1 = fmaxf(0.0f, fmaf(c2.y, f, c2.x));
+                    const float t = ds + MAGIC;            // round(d* - 1/2) = floor(d*) (ties: the extra tap has weight 0)
+                    const float f = ds - (t - MAGIC);      // frac(d*) - 1/2
+                    const int idx = __float_as_int(t) - MAGIC_BITS;
+                    const float w0 = fmaxf(0.0f, fmaf(-c2.x, f, c4.w));
+                    const float w1 = fmaxf(0.0f, fmaf(c2.x, f, c4.w));
                     float v0[V], v1[V];
                     unpack<V>(seg[idx], v0);
                     unpack<V>(seg[idx + 1], v1);
@@ -159,7 +173,8 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(BpParams p, Epi epi) {
                 }
             }
         }
-        __syncthreads();  // everyone is done with stage s before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s
     }
 
 #pragma unroll
@@ -183,7 +198,7 @@ inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cuda
         configured = true;
     }
     dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.R + BP_TH - 1) / BP_TH, groups);
-    bp_kernel<V, Epi><<<grid, BP_THREADS, smem, st>>>(p, epi);
+    bp_kernel<V, Epi><<<grid, BP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
 }
 

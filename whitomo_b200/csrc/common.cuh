@@ -21,7 +21,8 @@ constexpr int BP_TH = 32;
 constexpr int BP_AB = 16;
 constexpr int BP_STAGES = 3;
 constexpr int BP_SEGW = 80;  // floats per staged sinogram segment (>= tile extent + 7, multiple of 4)
-constexpr int BP_THREADS = 256;
+constexpr int BP_THREADS = 256;            // consumer threads
+constexpr int BP_BLOCK = BP_THREADS + 32;  // + one producer warp that only drives the TMA pipeline
 
 // ---- per-angle constants ------------------------------------------------------------------------
 // FP: position along the interpolation axis for line l and detector d is
@@ -112,6 +113,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(

@@ -61,7 +61,7 @@ struct FpEpiWhite {
                                                const float (&val)[V]) const {
         static_assert(V % K == 0, "group must hold whole slices");
         constexpr int SPG = V / K;
-        __shared__ float red[SPG][FP_THREADS / 32];
+        __shared__ float red[SPG][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.x;
@@ -100,7 +100,7 @@ struct FpEpiWhite {
             if (tid < SPG) {
                 float s = 0.0f;
 #pragma unroll
-                for (int w = 0; w < FP_THREADS / 32; ++w) s += red[tid][w];
+                for (int w = 0; w < FP_BLOCK / 32; ++w) s += red[tid][w];
                 partial[((size_t)g * SPG + tid) * nblocks + bid] = s;
             }
         }
@@ -120,7 +120,7 @@ struct FpEpiMar {
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
                                                const float (&val)[V]) const {
-        __shared__ float red[3][V][FP_THREADS / 32];
+        __shared__ float red[3][V][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.x;
@@ -156,7 +156,7 @@ struct FpEpiMar {
                 const int q = tid / V, i = tid % V;
                 float s = 0.0f;
 #pragma unroll
-                for (int w = 0; w < FP_THREADS / 32; ++w) s += red[q][i][w];
+                for (int w = 0; w < FP_BLOCK / 32; ++w) s += red[q][i][w];
                 partial[((size_t)q * nimg + (size_t)g * V + i) * nblocks + bid] = s;
             }
         }

@@ -23,7 +23,8 @@ namespace wt {
 
 constexpr int FP_DT = 32;       // detectors per CTA
 constexpr int FP_AT = 8;        // angles per CTA (one angle tile)
-constexpr int FP_THREADS = FP_DT * FP_AT;
+constexpr int FP_THREADS = FP_DT * FP_AT;  // consumer threads (one ray each)
+constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only drives the TMA pipeline
 constexpr int FP_LB = 16;       // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
 constexpr int FP_STAGES = 4;
@@ -118,14 +119,15 @@ template <int V>
 struct FpSmem {
     typedef typename VecOf<V>::T VecT;
     VecT seg[FP_STAGES][FP_LB][FP_W];
-    uint64_t full[FP_STAGES];
+    uint64_t full[FP_STAGES];   // TMA bytes of a stage have landed
+    uint64_t empty[FP_STAGES];  // all consumer warps are done reading a stage
     float wstart[FP_STAGES];
     float cmin[FP_AT], cmax[FP_AT], delta[FP_AT];  // per angle of the tile: position range at line 0, slope
     int lo, hi;                                    // line range any ray of the CTA needs
 };
 
 template <int V, class Epi>
-__global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
+__global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FpSmem<V> &sm = *reinterpret_cast<FpSmem<V> *>(smem_raw);
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
     const FpTile tile = p.tiles[blockIdx.y];
     const int a = tile.first + slot;
     const int g = blockIdx.z;
-    const bool valid = (slot < tile.count) && (d < p.D) && (a >= p.a_begin) && (a < p.a_end);
+    const bool producer = warp == FP_THREADS / 32;
+    const bool valid = !producer && (slot < tile.count) && (d < p.D) && (a >= p.a_begin) && (a < p.a_end);
 
     // orientation is uniform over the tile
     const FpAngle an0 = p.ang[tile.first];
@@ -149,7 +152,10 @@ __global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < FP_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < FP_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], FP_THREADS / 32);
+        }
         mbar_fence_init();
         sm.lo = nlines;
         sm.hi = 0;
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
     const int Lb = sm.lo, Le = sm.hi;
     const int nchunk = Le > Lb ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
 
-    // producer (warp 0): stage chunk `ch` = lines [Lb + ch*LB, +LB)
+    // producer warp: stage chunk `ch` = lines [Lb + ch*LB, +LB)
     auto produce = [&](int ch) {
         const int s = ch % FP_STAGES;
         const int l0 = Lb + ch * FP_LB;
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
         ws = (ws + VPAD) & ~(4 / V - 1);            // slot index (>= 0), 16-byte aligned
         const int nl = l1 - l0 + 1;
         if (lane == 0) {
+            fence_proxy_async();                     // consumers' generic-proxy reads of this stage precede the refill
             sm.wstart[s] = (float)(ws - VPAD);       // position of window slot 0
             mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nl * FP_W * sizeof(VecT)));
         }
@@ -231,44 +238,47 @@ __global__ void __launch_bounds__(FP_THREADS) fp_kernel(FpParams p, Epi epi) {
                         &sm.full[s]);
     };
 
-    if (warp == 0)
-        for (int b = 0; b < FP_STAGES - 1 && b < nchunk; ++b) produce(b);
-
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.0f;
     constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer
     constexpr int MAGIC_BITS = 0x4B400000;
 
-    for (int ch = 0; ch < nchunk; ++ch) {
-        const int s = ch % FP_STAGES;
-        if (warp == 0 && ch + FP_STAGES - 1 < nchunk) {
-            fence_proxy_async();
-            produce(ch + FP_STAGES - 1);
+    if (producer) {
+        // runs ahead of the consumers by up to FP_STAGES chunks; a stage is refilled as soon as all 8 consumer
+        // warps have released it -- consumer warps never wait for each other, only for data
+        for (int ch = 0; ch < nchunk; ++ch) {
+            if (ch >= FP_STAGES) mbar_wait(&sm.empty[ch % FP_STAGES], (uint32_t)(((ch / FP_STAGES) - 1) & 1));
+            produce(ch);
         }
-        mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
-        const int l0 = Lb + ch * FP_LB;
-        const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
-        if (la < lb) {
-            // c - 0.5 relative to the window start at line la; then one FADD per line
-            float cr = fmaf((float)la, delta, c0h) - sm.wstart[s];
-            const VecT *row = &sm.seg[s][la - l0][0];
+    } else {
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int s = ch % FP_STAGES;
+            mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
+            const int l0 = Lb + ch * FP_LB;
+            const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
+            if (la < lb) {
+                // c - 0.5 relative to the window start at line la; then one FADD per line
+                float cr = fmaf((float)la, delta, c0h) - sm.wstart[s];
+                const VecT *row = &sm.seg[s][la - l0][0];
 #pragma unroll 4
-            for (int l = la; l < lb; ++l) {
-                const float t = cr + MAGIC;                 // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
-                const float off = (cr - (t - MAGIC)) + 0.5f;
-                const int idx = __float_as_int(t) - MAGIC_BITS;
-                float v0[V], v1[V];
-                unpack<V>(row[idx], v0);
-                unpack<V>(row[idx + 1], v1);
-                const float w0 = 1.0f - off;
+                for (int l = la; l < lb; ++l) {
+                    const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
+                    const float off = (cr - (t - MAGIC)) + 0.5f;
+                    const int idx = __float_as_int(t) - MAGIC_BITS;
+                    float v0[V], v1[V];
+                    unpack<V>(row[idx], v0);
+                    unpack<V>(row[idx + 1], v1);
+                    const float w0 = 1.0f - off;
 #pragma unroll
-                for (int i = 0; i < V; ++i) acc[i] = fmaf(off, v1[i], fmaf(w0, v0[i], acc[i]));
-                cr += delta;
-                row += FP_W;
+                    for (int i = 0; i < V; ++i) acc[i] = fmaf(off, v1[i], fmaf(w0, v0[i], acc[i]));
+                    cr += delta;
+                    row += FP_W;
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with stage s
         }
-        __syncthreads();  // everyone is done with stage s before it is refilled
     }
 
     float val[V];
@@ -287,7 +297,7 @@ inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cuda
         configured = true;
     }
     dim3 grid((p.D + FP_DT - 1) / FP_DT, p.ntiles, groups);
-    fp_kernel<V, Epi><<<grid, FP_THREADS, smem, st>>>(p, epi);
+    fp_kernel<V, Epi><<<grid, FP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
 }
 
