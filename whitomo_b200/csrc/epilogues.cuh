@@ -257,8 +257,9 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
             if (prm.triv_w != 0.0f) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
             gt += prm.beta_reg * rg;
             if (f.use_bar) {
-                gt += f.bt * (-1.0f / v);
-                if (!f.lower_only) gt += f.bt * (1.0f / (1.0f - v));
+                // -1/x + 1/(1-x) = (2x - 1) / (x (1 - x)): one reciprocal; +-inf on the faces like the reference
+                if (f.lower_only) gt += f.bt * __fdividef(-1.0f, v);
+                else gt += f.bt * __fdividef(2.0f * v - 1.0f, v * (1.0f - v));
             }
             v = v - prm.alpha * gt;
         }
