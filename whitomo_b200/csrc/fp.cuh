@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const int a = tile.first + slot;
     const int g = blockIdx.z;
     const bool producer = warp == FP_THREADS / 32;
-    const bool valid = !producer && (slot < tile.count) && (d < p.D) && (a >= p.a_begin) && (a < p.a_end);
+    const bool intile = !producer && (slot < tile.count) && (d < p.D);
+    const bool valid = intile && (a >= p.a_begin) && (a < p.a_end);   // angle-range calls skip the other rays
 
     // orientation is uniform over the tile
     const FpAngle an0 = p.ang[tile.first];
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         // position range of the tile's rays of this angle at line 0 (detectors d0 .. min(d0+DT, D)-1)
         float lo_c = 3.0e38f, hi_c = -3.0e38f, dl = 0.0f;
         const int aa = tile.first + tid;
-        if (tid < tile.count && aa >= p.a_begin && aa < p.a_end) {
+        if (tid < tile.count) {
             const FpAngle an = p.ang[aa];
             const int dl_ = min(d0 + FP_DT, p.D) - 1;
             const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
 
     float c0h = 0.0f, delta = 0.0f, len = 0.0f;
     int l_lo = 0, l_hi = 0;
-    if (valid) {
+    if (intile) {
         const FpAngle an = p.ang[a];
         const float c0 = (float)(an.c0_base + ((double)d + 0.5) * an.c0_step);
         delta = an.delta;
@@ -199,14 +200,18 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
             l_lo = (int)fmaxf(floorf(fminf(t0, t1)), 0.0f);
             l_hi = (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)nlines);
         }
+        // chunk boundaries come from ALL rays of the tile, so that a ray's rounding sequence (and result bits)
+        // does not depend on which angle range a call asks for
         if (l_hi > l_lo) {
             atomicMin(&sm.lo, l_lo);
             atomicMax(&sm.hi, l_hi);
         }
+        if (!valid) l_lo = l_hi = 0;
     }
     __syncthreads();
     const int Lb = sm.lo, Le = sm.hi;
-    const int nchunk = Le > Lb ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
+    const bool tile_in_range = tile.first < p.a_end && tile.first + tile.count > p.a_begin;   // CTA-uniform
+    const int nchunk = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
 
     // producer warp: stage chunk `ch` = lines [Lb + ch*LB, +LB)
     auto produce = [&](int ch) {

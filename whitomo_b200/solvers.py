@@ -141,7 +141,7 @@ def _bc_project(proj, x, m, b_hb, n_iter=100, alpha=1e-2):
 
 
 def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t_step=0.2, alpha=0.1, beta_reg=1.0,
-                          max_iter=400, do_alpha_decay=False, with_sino_barrier=True, x0_level=1e-2):
+                          max_iter=400, do_alpha_decay=False, with_sino_barrier=True, x0_level=1e-2, on_outer=None):
     """Mono metal-artifact reduction of teeth_recon/experiments.py:651-749 on the device (defaults = its first run;
     the second run is n_iter=100, t0=0.1, max_iter=1000, do_alpha_decay=True, with_sino_barrier=False).
 
@@ -196,6 +196,8 @@ def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t
                 dirty = True
             if dirty:
                 u, st = fused_fp(t)
+        if on_outer is not None:
+            on_outer(dict(t=t, alpha=alpha, n_iter=n_iter, x=x, stats=st))
         t *= t_step
         if do_alpha_decay:
             alpha = alpha * math.sqrt(t_step)
