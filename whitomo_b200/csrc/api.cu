@@ -490,12 +490,17 @@ int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, 
     int bx = (int)((work + 255) / 256);
     if (bx > UPD_BLOCKS_PER_SLICE) bx = UPD_BLOCKS_PER_SLICE;
     dim3 grid(bx, nslices);
+    const bool fast = vec && n_elements == 2 && prm->reg_w != 0.0f && prm->t != 0.0f && !prm->lower_only &&
+                      prm->triv_w == 0.0f && (prm->elem_mask & 3u) == 3u && prm->mode == WT_UPD_STEP_CLIP;
 #define WT_UPD_LAUNCH(KK)                                                                                     \
-    if (vec) barrier_update_kernel<KK, 4><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial);         \
-    else barrier_update_kernel<KK, 1><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial)
+    if (vec) barrier_update_kernel<KK, 4, false><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial);  \
+    else barrier_update_kernel<KK, 1, false><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial)
     switch (n_elements) {
     case 1: WT_UPD_LAUNCH(1); break;
-    case 2: WT_UPD_LAUNCH(2); break;
+    case 2:
+        if (fast) barrier_update_kernel<2, 4, true><<<grid, 256, 0, st>>>(x, grad, npix, *prm, active, partial);
+        else { WT_UPD_LAUNCH(2); }
+        break;
     case 3: WT_UPD_LAUNCH(3); break;
     default: WT_UPD_LAUNCH(4); break;
     }

@@ -234,7 +234,7 @@ __global__ void reduce_partials_f64_kernel(const double *__restrict__ partial, i
 constexpr int UPD_BLOCKS_PER_SLICE = 296;  // 2 CTAs per SM worth of partials per slice
 
 struct UpdFlags {
-    bool act, clip, use_reg, use_bar, lower_only, want_pen;
+    bool act, clip, use_reg, use_bar, lower_only, want_pen, use_triv, all_elems, fast_log;
     float bt;
 };
 
@@ -250,11 +250,11 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         float v = xv[k];
-        if (f.act && ((prm.elem_mask >> k) & 1u)) {
+        if (f.act && (f.all_elems || ((prm.elem_mask >> k) & 1u))) {
             float gt = gv[k];
             float rg = 0.0f;
             if (f.use_reg) rg = prm.reg_w * (xv[K == 2 ? 1 - k : 0] * sgn);
-            if (prm.triv_w != 0.0f) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
+            if (f.use_triv) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
             gt += prm.beta_reg * rg;
             if (f.use_bar) {
                 // -1/x + 1/(1-x) = (2x - 1) / (x (1 - x)): one reciprocal; +-inf on the faces like the reference
@@ -278,7 +278,7 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
                 // -log(x) - log(1-x) = -log(x (1-x)); +inf on (or outside) the boundary like phi[f >= 0] = inf
                 const float arg = f.lower_only ? xn[k] : xn[k] * (1.0f - xn[k]);
                 const bool inside = f.lower_only ? (xn[k] > 0.0f) : (xn[k] > 0.0f && xn[k] < 1.0f);
-                ph += inside ? -logf(arg) : INFINITY;
+                ph += inside ? -(f.fast_log ? __logf(arg) : logf(arg)) : INFINITY;
             }
             pen = f.bt * ph;
         }
@@ -289,7 +289,9 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
 
 // VEC = 4: every thread owns 4 consecutive pixels (16-byte loads/stores), VEC = 1: scalar fallback for
 // pixel counts that are not a multiple of 4.  grid = (blocks per slice, slices).
-template <int K, int VEC>
+// FAST: the flag set of the white-beam box-barrier iteration (K = 2 with the |c0 c1| regulariser, both barrier
+// faces, all elements, step + clip) is fixed at compile time so that the per-element code is branch-free.
+template <int K, int VEC, bool FAST>
 __global__ void __launch_bounds__(256) barrier_update_kernel(float *__restrict__ x, const float *__restrict__ grad,
                                                              size_t npix, wt_update_params prm,
                                                              const unsigned char *__restrict__ active, double *partial) {
@@ -299,11 +301,14 @@ __global__ void __launch_bounds__(256) barrier_update_kernel(float *__restrict__
     const float *gs = grad ? grad + slice * K * npix : nullptr;
     UpdFlags f;
     const bool sl_on = !active || active[slice];
-    f.act = sl_on && prm.mode != WT_UPD_CLIP_ONLY;
-    f.clip = sl_on && prm.mode != WT_UPD_STEP_ONLY;
-    f.use_reg = (K == 2) && prm.reg_w != 0.0f;
-    f.use_bar = prm.t != 0.0f;
-    f.lower_only = prm.lower_only != 0;
+    f.act = FAST ? sl_on : (sl_on && prm.mode != WT_UPD_CLIP_ONLY);
+    f.clip = FAST ? sl_on : (sl_on && prm.mode != WT_UPD_STEP_ONLY);
+    f.use_reg = FAST ? true : ((K == 2) && prm.reg_w != 0.0f);
+    f.use_bar = FAST ? true : (prm.t != 0.0f);
+    f.lower_only = FAST ? false : (prm.lower_only != 0);
+    f.use_triv = FAST ? false : (prm.triv_w != 0.0f);
+    f.all_elems = FAST ? true : ((prm.elem_mask & ((1u << K) - 1u)) == ((1u << K) - 1u));
+    f.fast_log = FAST;
     f.want_pen = partial != nullptr;
     f.bt = prm.beta_reg * prm.t;
     const bool writes = f.act || f.clip;
