@@ -32,6 +32,15 @@ UNIT = "GUPS (1e9 pixel*angle updates/s, K FP + K BP of each barrier iteration)"
 WORKLOAD = "C4: white-beam log-barrier iteration, 2048x2048 slices, 1800 angles, D=2897, K=2, E=64"
 
 
+def onchip_ceiling():
+    """measured shared-memory ceiling of K1/K2 in GUPS (tools/smem_peak.cu -> profiles/ONCHIP_PEAKS.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ONCHIP_PEAKS.json")) as f:
+            return float(json.load(f)["gups_ceiling_v4"]), "measured"
+    except Exception:
+        return 4653.1, "nominal"
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -307,6 +316,7 @@ def run_gpu(args):
     t_bp = float(np.mean([m[1].elapsed_time(m[2]) for m in marks])) * 1e-3
     t_up = float(np.mean([m[2].elapsed_time(m[3]) for m in marks])) * 1e-3
     hbm, which = peaks()
+    ceil_gups, ceil_src = onchip_ceiling()
     # algorithmic bytes per launch: fused white FP reads K*N^2 + A*D (meas), writes K*A*D (q*mu)
     fp_bytes = 4.0 * (K * N * N + A * D + K * A * D) * S
     bp_bytes = 4.0 * (K * A * D + K * N * N) * S
@@ -324,6 +334,9 @@ def run_gpu(args):
         "barrier_iters_per_s": S * world * args.steps / elapsed,
         "fp_gups": K * N * N * A * S / t_fp / 1e9, "bp_gups": K * N * N * A * S / t_bp / 1e9,
         "kernel_ms": {"white_fp": t_fp * 1e3, "bp": t_bp * 1e3, "barrier_update": t_up * 1e3},
+        "onchip": {"bound": "shared-memory load bandwidth (2 taps x 16 B per 4 updates)", "peak_gups": ceil_gups,
+                   "peak_source": ceil_src, "fp_frac": K * N * N * A * S / t_fp / 1e9 / ceil_gups,
+                   "bp_frac": K * N * N * A * S / t_bp / 1e9 / ceil_gups},
         "roofline": dict(roof(fp_bytes, t_fp), kernel="fp_kernel<4, white epilogue> (dominant: %.0f%% of the step)"
                          % (100 * t_fp / (t_fp + t_bp + t_up)),
                          note="gather/stencil kernel with ~N-fold on-chip reuse: bound by L1/LSU issue, not HBM "

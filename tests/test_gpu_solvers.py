@@ -194,3 +194,29 @@ def test_fp_angle_range_and_angle_split_single_rank():
     assert sp.range == (0, 40) and torch.equal(sp.fp(x), full)
     y = torch.rand(40, 69, device="cuda")
     assert torch.equal(sp.bp(y), P.bp(y))
+
+
+def test_stack_reconstruction_in_resident_batches(golden):
+    """C4-style job at toy size: 7 host-resident slices, batches of 3, two 'ranks' -- every slice must come out
+    bit-identical to reconstructing the whole stack in one resident batch (slices are independent, and a slice's
+    result does not depend on which float4 group it shares)."""
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    grid = z["grid"]
+    P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    sp = Spectrum(z["source"] / np.sum(z["source"] * grid[:, 1]), grid[:, 1], z["ea"], float(z["pixel_size"]))
+    rng = np.random.default_rng(3)
+    S = 7
+    gts = np.stack([np.clip(z["gt"] * rng.uniform(0.5, 1.0), 0, 1) for _ in range(S)]).astype(np.float32)
+    meas = P.white_fp(sp, torch.from_numpy(gts).cuda(), want_qmu=False, want_loss=False)[0].cpu().pin_memory()
+    x0 = torch.from_numpy(np.stack([z["x0"] * rng.uniform(0.8, 1.2) for _ in range(S)]).astype(np.float32)).pin_memory()
+    p = dict(n_iter=4, n_biter=2, t0=0.1, t_step=0.5, alpha=0.3, ir_beta=0.05, max_iter=10, n_steps_without_progress=None)
+    whole, _ = solvers.white_barrier_stack(P, sp, meas.cuda(), x0.cuda(), **p)
+    parts = []
+    for rank in range(2):
+        out, (s0, s1) = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, rank=rank, world=2, **p)
+        assert (s0, s1) == ((0, 4), (4, 7))[rank]
+        parts.append(out)
+    assert torch.equal(torch.cat(parts), whole.cpu())

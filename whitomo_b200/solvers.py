@@ -203,3 +203,42 @@ def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t
             alpha = alpha * math.sqrt(t_step)
             n_iter = min(int(n_iter / t_step), max_iter)
     return x.reshape(lead + proj.vol_shape)
+
+
+def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=0, world=1, **params):
+    """The C4 job: a stack of independent slices (host memory) reconstructed in resident batches on this rank's GPU.
+
+    meas_host (S, A, D) and x0_host (S, K, N, N) are CPU tensors (pinned memory makes the copies asynchronous).  The
+    rank takes the contiguous slice range ``shard_range(S, rank, world)`` -- no collective is involved -- uploads
+    ``batch`` slices at a time on a copy stream while the previous batch iterates, runs ALL barrier iterations of a
+    batch while it is resident (slices are independent, so nothing else ever needs to be on the device), and writes
+    the result into the returned CPU tensor.  ``params`` are those of ``white_barrier_stack``.
+    Returns (x_host for the rank's range, (start, stop))."""
+    from .distributed import shard_range
+    s0, s1 = shard_range(meas_host.shape[0], rank, world)
+    out = torch.empty((s1 - s0,) + tuple(x0_host.shape[1:]), dtype=torch.float32,
+                      pin_memory=meas_host.is_pinned())
+    dev = proj.device
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def upload(b0):
+        b1 = min(b0 + batch, s1)
+        with torch.cuda.stream(copy_stream):
+            m = meas_host[b0:b1].to(dev, non_blocking=True)
+            x = x0_host[b0:b1].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        return b0, b1, m, x, ev
+
+    nxt = upload(s0) if s1 > s0 else None
+    while nxt is not None:
+        b0, b1, m, x, ev = nxt
+        nxt = upload(b1) if b1 < s1 else None            # overlaps the iterations below
+        main.wait_event(ev)
+        m.record_stream(main)
+        x.record_stream(main)
+        res, _ = white_barrier_stack(proj, spectrum, m, x, **params)
+        out[b0 - s0:b1 - s0].copy_(res, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    return out, (s0, s1)
