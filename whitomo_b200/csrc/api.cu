@@ -410,7 +410,7 @@ int wt_spectrum_create(int n_elements, int n_bins, const double *source, const d
     std::vector<float> tab((size_t)(n_elements + 1) * n_bins);
     for (int e = 0; e < n_bins; ++e) tab[e] = (float)(source[e] * widths[e]);
     for (int k = 0; k < n_elements; ++k)
-        for (int e = 0; e < n_bins; ++e) tab[(size_t)(k + 1) * n_bins + e] = (float)(pixel_size * absorptions[(size_t)k * n_bins + e]);
+        for (int e = 0; e < n_bins; ++e) tab[(size_t)(k + 1) * n_bins + e] = (float)(pixel_size * absorptions[(size_t)k * n_bins + e] * 1.4426950408889634);
     wt_spectrum *s = new wt_spectrum();
     s->K = n_elements; s->E = n_bins; s->d_tab = nullptr;
     cudaError_t e = cudaMalloc(&s->d_tab, tab.size() * sizeof(float));

@@ -65,7 +65,7 @@ struct wt_geom {
 
 struct wt_spectrum {
     int K, E;
-    float *d_tab;  // [E] s_e*w_e, then K rows [E] of pix*ea[k,e]
+    float *d_tab;  // [E] s_e*w_e, then K rows [E] of pix*ea[k,e]*log2(e)  (the kernels use exp2)
 };
 
 namespace wt {

@@ -13,7 +13,7 @@ struct FpEpiSirtResidual {
     float *out;           // (n, A, D)
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V]) const {
+                                               const float (&val)[V], float *) const {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const float rs = __ldg(raysum + r);
@@ -50,7 +50,7 @@ __global__ void fill_kernel(float *p, size_t n, float v) {
 // A group of V interleaved images holds V/K slices x K elements (image index = slice*K + k).
 template <int K>
 struct FpEpiWhite {
-    const float *tab;   // [E] s_e*w_e, then K x [E] pix*ea[k][e]
+    const float *tab;   // [E] s_e*w_e, then K x [E] pix*ea[k][e]*log2(e)
     int E;
     const float *meas;  // (S, A, D) or null
     float *inten;       // (S, A, D) or null
@@ -58,13 +58,21 @@ struct FpEpiWhite {
     float *partial;     // (S, nblocks) per-CTA sums of q^2, or null
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V]) const {
+                                               const float (&val)[V], float *scratch) const {
         static_assert(V % K == 0, "group must hold whole slices");
         constexpr int SPG = V / K;
         __shared__ float red[SPG][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.x;
+        // spectrum tables -> shared memory (the projector's staging buffers are idle now): broadcast LDS in the bin loop
+        const int ntab = (K + 1) * E;
+        const bool in_smem = ntab * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);
+        __syncthreads();
+        if (in_smem)
+            for (int i = tid; i < ntab; i += FP_BLOCK) scratch[i] = __ldg(tab + i);
+        __syncthreads();
+        const float *tb = in_smem ? scratch : tab;
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
@@ -76,17 +84,17 @@ struct FpEpiWhite {
                 for (int e = 0; e < E; ++e) {
                     float arg = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) arg = fmaf(__ldg(tab + (k + 1) * E + e), val[sl * K + k], arg);
-                    const float t = __ldg(tab + e) * expf(-arg);
+                    for (int k = 0; k < K; ++k) arg = fmaf(tb[(k + 1) * E + e], val[sl * K + k], arg);
+                    const float t = tb[e] * exp2f(-arg);     // tables are pre-scaled by log2(e): one MUFU.EX2
                     I += t;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, __ldg(tab + (k + 1) * E + e), mu[k]);
+                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, tb[(k + 1) * E + e], mu[k]);
                 }
                 const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
                 if (inten) inten[slice * plane + r] = I;
                 if (qmu) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-mu[k]);
+                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-0.6931471805599453f * mu[k]);
                 }
                 q2 = q * q;
             }
@@ -119,7 +127,7 @@ struct FpEpiMar {
     int nimg;                    // n of this launch (stride of the partial planes)
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V]) const {
+                                               const float (&val)[V], float *) const {
         __shared__ float red[3][V][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
@@ -175,7 +183,7 @@ __global__ void white_epilogue_kernel(const float *__restrict__ P, const float *
         for (int e = 0; e < E; ++e) {
             float arg = 0.0f;
             for (int k = 0; k < K; ++k) arg = fmaf(__ldg(tab + (k + 1) * E + e), __ldg(P + (slice * K + k) * plane + r), arg);
-            I += __ldg(tab + e) * expf(-arg);
+            I += __ldg(tab + e) * exp2f(-arg);
         }
         const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
         if (inten) inten[slice * plane + r] = I;
@@ -186,9 +194,9 @@ __global__ void white_epilogue_kernel(const float *__restrict__ P, const float *
                     float arg = 0.0f;
                     for (int kk = 0; kk < K; ++kk)
                         arg = fmaf(__ldg(tab + (kk + 1) * E + e), __ldg(P + (slice * K + kk) * plane + r), arg);
-                    mu = fmaf(__ldg(tab + e) * expf(-arg), __ldg(tab + (k + 1) * E + e), mu);
+                    mu = fmaf(__ldg(tab + e) * exp2f(-arg), __ldg(tab + (k + 1) * E + e), mu);
                 }
-                qmu[(slice * K + k) * plane + r] = q * (-mu);
+                qmu[(slice * K + k) * plane + r] = q * (-0.6931471805599453f * mu);
             }
         }
         q2 = q * q;

@@ -107,7 +107,7 @@ struct FpEpiStore {
     float *sino;
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V]) const {
+                                               const float (&val)[V], float *) const {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D;
 #pragma unroll
@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     float val[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) val[i] = acc[i] * len;
-    epi.template operator()<V>(p, g, a, d, valid, val);
+    // the staging buffers are free now: epilogues may use them as CTA scratch (after their own __syncthreads)
+    epi.template operator()<V>(p, g, a, d, valid, val, reinterpret_cast<float *>(&sm.seg[0][0][0]));
 }
 
 template <int V, class Epi>
