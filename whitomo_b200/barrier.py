@@ -1,14 +1,14 @@
-"""Drop-in for ``teeth_recon/barrier.py``: ``HoughBarrier``, the log-barrier on the sinogram domain
-(constraint FP(x)[m] >= b for the photon-starved rays of a metal shadow).
+"""Drop-in for ``teeth_recon/barrier.py``: ``HoughBarrier``, the log-barrier on the sinogram ("Hough") domain --
+the constraint FP(x)[m] >= b for the photon-starved rays ``m`` of a metal shadow, i.e. f(x) = b - FP(x)[m] <= 0.
 
-``FP`` / ``BP`` are the caller's closures (flat in, flat out) exactly as in the reference; they may be
-numpy closures over ``astra_proxy.gpu_fp`` or torch closures over ``Projector.fp`` -- the class works on
-either array type.  The fused device loop for the mono MAR scenario lives in ``whitomo_b200.solvers``.
+``FP`` / ``BP`` are the caller's closures (flat in, flat out) exactly as in the reference; they may be numpy
+closures over ``astra_proxy.gpu_fp`` or torch closures over ``Projector.fp`` -- the class works on either array
+type.  The fused device loop for the mono MAR scenario lives in ``whitomo_b200.solvers``.
 """
 import numpy as np
 
 from . import barrier_method
-from .barrier_method import _is_tensor, _copy
+from .barrier_method import _is_tensor, _copy, _neg_log_barrier
 
 try:
     import torch
@@ -16,63 +16,56 @@ except ImportError:  # pragma: no cover
     torch = None
 
 
-def _zeros_like_flat(r):
-    if _is_tensor(r):
-        return torch.zeros_like(r).flatten()
-    return np.zeros_like(r).flatten()
-
-
 class HoughBarrier(barrier_method.BarrierFunction):
+    #: Landweber-like feasibility projection (teeth_recon/barrier.py:30): at most this many steps of this size
+    PROJECT_STEPS = 100
+    PROJECT_STEP_SIZE = 1e-2
+
     def __init__(self, FP, BP, m, b, r_like):
-        self.FP = FP
-        self.BP = BP
-        self.m = m
-        self.b = b
-        self.r = r_like
+        self.FP, self.BP, self.m, self.b, self.r = FP, BP, m, b, r_like
+        super(HoughBarrier, self).__init__(self._constraint, self._constraint_grad, self._project_feasible)
 
-        def bc_func(x):
-            return b - FP(x)[m]
+    # ---- the (func, grad, proj) triple BarrierFunction expects --------------------------------------------
+    def _sino_zeros(self):
+        z = torch.zeros_like(self.r) if _is_tensor(self.r) else np.zeros_like(self.r)
+        return z.flatten()
 
-        def bc_grad(x):
-            grad = _zeros_like_flat(r_like)       # the reference reads an undefined name here (B10)
-            grad[m] = -1
-            return BP(grad)
+    def _constraint(self, x):
+        return self.b - self.FP(x)[self.m]
 
-        def bc_project(x, n_iter=100, alpha=1e-2):
-            """teeth_recon/barrier.py:30-45 -- Landweber-like steps on the violated rays only (B11 kept)."""
-            f = FP(x)
-            x_new = _copy(x)
-            for _ in range(n_iter):
-                infeas_i = m & (f < b)
-                if not bool(infeas_i.any()):
-                    break
-                f[~infeas_i] = 0
-                f[infeas_i] -= b + 1e-3
-                x_new = x_new - alpha * BP(f)
-                f = FP(x_new)
-            return x_new
+    def _constraint_grad(self, x):
+        ones_on_mask = self._sino_zeros()          # the reference reads an undefined name here (B10)
+        ones_on_mask[self.m] = -1
+        return self.BP(ones_on_mask)
 
-        super(HoughBarrier, self).__init__(bc_func, bc_grad, bc_project)
+    def _project_feasible(self, x, n_iter=None, alpha=None):
+        """Push x towards {FP(x)[m] >= b}: repeat x -= alpha * BP(residual of the violated rays), where the
+        residual is FP(x) - (b + 1e-3) on the violated rays and 0 elsewhere (the reference's literal update,
+        teeth_recon/barrier.py:36-43, B11)."""
+        n_iter = self.PROJECT_STEPS if n_iter is None else n_iter
+        alpha = self.PROJECT_STEP_SIZE if alpha is None else alpha
+        proj = self.FP(x)
+        out = _copy(x)
+        for _ in range(n_iter):
+            violated = self.m & (proj < self.b)
+            if not bool(violated.any()):
+                break
+            proj[~violated] = 0
+            proj[violated] -= self.b + 1e-3
+            out = out - alpha * self.BP(proj)
+            proj = self.FP(out)
+        return out
 
+    # ---- evaluation with ONE forward and ONE back projection (teeth_recon/barrier.py:50-69) ----------------
     def eval(self, x, do_grad=True):
-        fp = self.FP(x)
-        fx = self.b - fp[self.m]
-        if _is_tensor(fx):
-            phi = -torch.log(-fx)
-            phi = torch.where(fx >= 0, torch.full_like(phi, float('inf')), phi)
-        else:
-            with np.errstate(invalid='ignore', divide='ignore'):
-                phi = -np.log(-fx)
-            phi[fx >= 0] = np.inf
-        self.last_f = fx
-        self.last_phi = phi
+        self.last_f = self.b - self.FP(x)[self.m]
+        self.last_phi = _neg_log_barrier(self.last_f)
         self.num_feval += 1
-        grad_phi = None
-        if do_grad:
-            grad = _zeros_like_flat(self.r)
-            grad[self.m] = -1 / fx
-            grad_phi = -self.BP(grad)
-            self.last_g = grad
-            self.last_grad = grad_phi
-            self.num_geval += 1
-        return (phi, grad_phi)
+        if not do_grad:
+            return (self.last_phi, None)
+        weights = self._sino_zeros()
+        weights[self.m] = -1 / self.last_f
+        self.last_g = weights
+        self.last_grad = -self.BP(weights)
+        self.num_geval += 1
+        return (self.last_phi, self.last_grad)

@@ -1,16 +1,17 @@
 """Drop-in for ``src/barrier_method.py``: gradient descent on  f + beta*sum(reg) + beta*t*sum(phi),
 phi = -log(-g(x)), with t shrinking by ``t_step`` per outer iteration and a projection onto the feasible
-set after every step.  Same signature, same return value ``(x, opt_stats)``.
+set after every step.  Same public names (``StepStat``, ``BarrierFunction``, ``barrier_method``),
+same signature, same return value ``(x, opt_stats)``.
 
-The driver is array-library agnostic: it only uses ``+ - *``, ``.copy()``/``.clone()`` and reductions that
-both numpy arrays and torch (CUDA) tensors provide, so the closures may keep everything on the device (see
-``whitomo_b200.solvers`` for the fused device loops that implement the reference's two concrete scenarios
-with K FP + K BP per inner iteration instead of 3K FP + K BP).
+The driver is array-library agnostic: the closures may work on numpy arrays or on torch (CUDA) tensors, so a
+caller can keep the whole loop on the device (``whitomo_b200.solvers`` holds the fused device loops for the
+reference's two concrete scenarios, which spend K FP + K BP per inner iteration instead of 3K FP + K BP).
 
-Py3 fixes behind the same behaviour: ``.items()`` for ``.iteritems()`` (B3), barriers
-without a projection are skipped via ``project`` (B4).  Kept on purpose: the gradient returned by
-``goal_function[1]`` is modified in place (B5); the stats callback fires on every inner iteration because
-``glob_iter`` only advances per outer iteration (B6); ``n_iter`` grows only under ``do_alpha_decay`` (B7).
+Behaviour kept on purpose: the array returned by the goal gradient is accumulated into in
+place, so the goal ``StepStat.grad`` is the total gradient (B5); the statistics callback fires on every inner
+iteration because the counter that gates it only advances per outer iteration (B6); the inner iteration count
+grows only together with the step decay (B7).  Fixed: dict iteration is py3 (B3), a barrier without a
+projection is skipped instead of raising (B4).
 """
 from __future__ import print_function, division
 
@@ -38,42 +39,42 @@ def _copy(x):
 
 
 def _total(x):
-    """sum over all elements as a python float / 0-d value (np.sum(np.ravel(.)) in the reference)."""
-    if _is_tensor(x):
-        return x.sum().item()
-    return np.sum(np.ravel(x))
+    """sum over all elements, as the reference's np.sum(np.ravel(.))"""
+    return x.sum().item() if _is_tensor(x) else np.sum(np.ravel(x))
+
+
+def _neg_log_barrier(fx):
+    """-log(-f) with +inf (not nan) wherever the constraint f <= 0 is violated or active"""
+    if _is_tensor(fx):
+        phi = -torch.log(-fx)
+        return torch.where(fx >= 0, torch.full_like(phi, float('inf')), phi)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        phi = -np.log(-fx)
+    phi[fx >= 0] = np.inf
+    return phi
 
 
 class BarrierFunction(object):
-    """phi(x) = -log(-f(x)) for the constraint f(x) <= 0  (src/barrier_method.py:14-77)."""
+    """Barrier penalty phi(x) = -log(-f(x)) of one constraint f(x) <= 0 (src/barrier_method.py:14-77).
+
+    ``func`` / ``grad`` evaluate f and its gradient, ``proj`` (optional) maps a point onto the feasible set.
+    ``eval`` caches ``last_f``, ``last_phi``, ``last_g``, ``last_grad`` for the statistics callback and counts
+    evaluations in ``num_feval`` / ``num_geval`` like the reference."""
 
     def __init__(self, func, grad, proj=None):
-        self.f = func
-        self.g = grad
-        self.num_feval = 0
-        self.num_geval = 0
-        self.proj = proj
+        self.f, self.g, self.proj = func, grad, proj
+        self.num_feval = self.num_geval = 0
 
     def eval(self, x, do_grad=True):
-        fx = self.f(x)
-        if _is_tensor(fx):
-            phi = -torch.log(-fx)
-            phi = torch.where(fx >= 0, torch.full_like(phi, float('inf')), phi)
-        else:
-            with np.errstate(invalid='ignore', divide='ignore'):
-                phi = -np.log(-fx)
-            phi[fx >= 0] = np.inf          # infeasible points: inf instead of nan
-        self.last_f = fx
-        self.last_phi = phi
+        self.last_f = self.f(x)
+        self.last_phi = _neg_log_barrier(self.last_f)
         self.num_feval += 1
-        grad_phi = None
-        if do_grad:
-            gx = self.g(x)
-            grad_phi = -gx / fx
-            self.last_g = gx
-            self.last_grad = grad_phi
-            self.num_geval += 1
-        return (phi, grad_phi)
+        if not do_grad:
+            return (self.last_phi, None)
+        self.last_g = self.g(x)
+        self.last_grad = -self.last_g / self.last_f
+        self.num_geval += 1
+        return (self.last_phi, self.last_grad)
 
     def func(self, x):
         return self.eval(x, do_grad=False)[0]
@@ -85,9 +86,43 @@ class BarrierFunction(object):
         return bool((self.f(x) <= 0).all())
 
     def project(self, x):
-        if self.proj is None:
-            return x
-        return self.proj(x)
+        return x if self.proj is None else self.proj(x)
+
+
+def _as_barriers(ineq_dict):
+    """{name: (g, grad g[, proj]) | BarrierFunction} -> ordered {name: BarrierFunction}"""
+    out = collections.OrderedDict()
+    for name, spec in ineq_dict.items():
+        if type(spec) is tuple:
+            out[name] = BarrierFunction(*spec)
+        elif isinstance(spec, BarrierFunction):
+            out[name] = spec
+    return out
+
+
+def _make_feasible(x0, barriers):
+    """src/barrier_method.py:128-152: one projection attempt; returns (x0, ok)"""
+    if all(b.is_feasible(x0) for b in barriers.values()):
+        return x0, True
+    print('WARNING! the initial guess is not feasible.')
+    print('trying to project in onto fieasible set..')
+    for b in barriers.values():
+        x0 = b.project(x0)
+    failed = [name for name, b in barriers.items() if not b.is_feasible(x0)]
+    if failed:
+        print('ERROR! feasibility projection unsuccesfull')
+        print('non-satisfied constraints: ', ' '.join(failed))
+    return x0, not failed
+
+
+def _penalised_loss(x, goal_function, reg_dict, barriers, beta_reg, t):
+    """f(x) + sum beta*reg(x) + sum beta*t*phi(x), every term summed over all elements (:208-213)"""
+    loss = goal_function[0](x)
+    for r in reg_dict.values():
+        loss += _total(beta_reg * r[0](x))
+    for b in barriers.values():
+        loss += _total(beta_reg * t * b.func(x))
+    return loss
 
 
 def barrier_method(x0, goal_function, reg_dict={}, ineq_dict={}, n_iter=200, t0=1.0, n_biter=10, alpha=0.1,
@@ -96,90 +131,63 @@ def barrier_method(x0, goal_function, reg_dict={}, ineq_dict={}, n_iter=200, t0=
                    do_alpha_decay=True,
                    min_delta_loss=1e-3,
                    n_steps_without_progress=None):
-    """Minimise ``goal_function`` = (f, grad f) with regularisers ``reg_dict`` = {name: (r, grad r)} subject to
-    ``ineq_dict`` = {name: (g, grad g[, proj]) | BarrierFunction} (constraints g(x) <= 0).
-    Parameters and semantics as in src/barrier_method.py:79-116."""
-    bf_objs = collections.OrderedDict()
-    bf = collections.OrderedDict()
-    for k, v in ineq_dict.items():
-        if type(v) is tuple:
-            v = BarrierFunction(*v)
-        elif not isinstance(v, BarrierFunction):
-            continue
-        bf_objs[k] = v
-        bf[k] = (v.func, v.grad)
+    """Minimise ``goal_function`` = (f, grad f) plus regularisers ``reg_dict`` = {name: (r, grad r)} subject to the
+    inequality constraints of ``ineq_dict`` (g(x) <= 0).  Parameters as in src/barrier_method.py:84-116:
+    ``n_biter`` barrier levels starting at ``t0`` and shrinking by ``t_step``; ``n_iter`` gradient steps of size
+    ``alpha`` per level; with ``do_alpha_decay`` the step shrinks by sqrt(t_step) and the number of steps grows by
+    1/t_step (capped at ``max_iter``) per level; a level is left early after ``n_steps_without_progress`` steps
+    whose loss decrease stays below ``min_delta_loss``.  Returns ``(x, [])`` or ``(x0, None)`` when the start
+    cannot be made feasible."""
+    barriers = _as_barriers(ineq_dict)
+    x, ok = _make_feasible(x0, barriers)
+    if not ok:
+        return x, None
 
-    # the initial guess must be feasible; one projection attempt, else (x0, None) like the reference
-    if not all(v.is_feasible(x0) for v in bf_objs.values()):
-        print('WARNING! the initial guess is not feasible.')
-        print('trying to project in onto fieasible set..')
-        for v in bf_objs.values():
-            x0 = v.project(x0)
-        infeas_list = [k for k, v in bf_objs.items() if not v.is_feasible(x0)]
-        if infeas_list:
-            print('ERROR! feasibility projection unsuccesfull')
-            print('non-satisfied constraints: ', ' '.join(infeas_list))
-            return x0, None
-
-    t = t0
-    x = x0
     opt_stats = []
-    glob_iter = 0
-    for i_biter in range(n_biter):
-        prev_loss = None
-        no_progress_count = 0
-        print('starting ', i_biter, 'barrier iteration.')
-        for i_iter in range(n_iter):
-            goal_grad = goal_function[1](x)
-            reg_grads = collections.OrderedDict((k, v[1](x)) for k, v in reg_dict.items())
-            bf_grads = collections.OrderedDict((k, v[1](x)) for k, v in bf.items())
+    t = t0
+    stats_gate = 0            # the reference's glob_iter: advanced once per barrier level
+    for level in range(n_biter):
+        print('starting ', level, 'barrier iteration.')
+        last_loss, stalled = None, 0
+        for step_no in range(n_iter):
+            total = goal_function[1](x)            # accumulated into in place below (B5)
+            reg_parts = collections.OrderedDict((name, r[1](x)) for name, r in reg_dict.items())
+            bar_parts = collections.OrderedDict((name, b.grad(x)) for name, b in barriers.items())
+            goal_part = total
+            for part in reg_parts.values():
+                total += beta_reg * part
+            for part in bar_parts.values():
+                total += beta_reg * part * t
 
-            grad = goal_grad                      # same object: accumulated in place (B5)
-            for g in reg_grads.values():
-                grad += beta_reg * g
-            for g in bf_grads.values():
-                grad += beta_reg * g * t
-            step = -alpha * grad
+            helpers.printProgressBar(step_no, n_iter - 1, prefix='barrier iter %d/%d' % (level + 1, n_biter),
+                                     suffix='done (%03d/%03d)' % (step_no + 1, n_iter), length=50)
 
-            helpers.printProgressBar(i_iter, n_iter - 1,
-                                     prefix='barrier iter %d/%d' % (i_biter + 1, n_biter),
-                                     suffix='done (%03d/%03d)' % (i_iter + 1, n_iter), length=50)
+            if add_stat_cb is not None and (stats_gate % 10 == 0 or stats_gate < 30):
+                snap = _copy(x)
+                add_stat_cb((StepStat(snap, goal_function[0](x), _copy(goal_part)),
+                             {name: StepStat(snap, r[0](x), _copy(reg_parts[name])) for name, r in reg_dict.items()},
+                             {name: StepStat(snap, _copy(b.last_phi), _copy(b.last_grad)) for name, b in barriers.items()}))
 
-            if add_stat_cb is not None and (glob_iter % 10 == 0 or glob_iter < 30):
-                x_stat = _copy(x)
-                goal_stat = StepStat(x_stat, goal_function[0](x), _copy(goal_grad))
-                reg_stats = {k: StepStat(x_stat, v[0](x), _copy(reg_grads[k])) for k, v in reg_dict.items()}
-                bf_stats = {k: StepStat(x_stat, _copy(v.last_phi), _copy(v.last_grad)) for k, v in bf_objs.items()}
-                add_stat_cb((goal_stat, reg_stats, bf_stats))
+            x = x + (-alpha * total)
+            for b in barriers.values():            # projection after every step (:203-206)
+                x = b.project(x)
 
-            x = x + step
-            for v in bf_objs.values():            # projection after every step
-                x = v.project(x)
+            if n_steps_without_progress is None:
+                continue
+            loss = _penalised_loss(x, goal_function, reg_dict, barriers, beta_reg, t)
+            if last_loss is not None:
+                stalled = 0 if last_loss - loss >= min_delta_loss else stalled + 1
+            last_loss = loss
+            if stalled >= n_steps_without_progress:
+                print('\nstopping barrier step', level, 'on iteration', step_no,
+                      'because there was no valuable progress')
+                break
 
-            if n_steps_without_progress is not None:
-                loss = goal_function[0](x)
-                for v in reg_dict.values():
-                    loss += _total(beta_reg * v[0](x))
-                for v in bf.values():
-                    loss += _total(beta_reg * t * v[0](x))
-                if prev_loss is not None:
-                    if prev_loss - loss >= min_delta_loss:
-                        no_progress_count = 0
-                    else:
-                        no_progress_count += 1
-                prev_loss = loss
-                if no_progress_count >= n_steps_without_progress:
-                    print('\nstopping barrier step', i_biter, 'on iteration', i_iter,
-                          'because there was no valuable progress')
-                    break
-
-        t = t * t_step
+        t *= t_step
         if do_alpha_decay:
-            alpha = alpha * math.sqrt(t_step)
-            n_iter = int(n_iter / t_step)
-            if n_iter > max_iter:
-                n_iter = max_iter
+            alpha *= math.sqrt(t_step)
+            n_iter = min(int(n_iter / t_step), max_iter)
         print('')
-        glob_iter += 1
+        stats_gate += 1
 
     return x, opt_stats
