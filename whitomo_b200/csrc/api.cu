@@ -297,11 +297,17 @@ int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles
 
 size_t wt_workspace_bytes(const wt_geom *g, int nimages) {
     if (!g || nimages <= 0) return 0;
+    if (nimages == 1) nimages = 2;   // a single image is packed as a mirror pair
     size_t fl = packed_vol_floats(g, nimages) + packed_sino_floats(g, nimages);
     fl += align_up((size_t)3 * nimages * fp_blocks(g), 64);                  // per-CTA partials (float)
     size_t bytes = fl * sizeof(float) + align_up((size_t)nimages * UPD_BLOCKS_PER_SLICE * sizeof(double), 256);
     return bytes + 4096;
 }
+
+static int run_fp_mirror(const wt_geom *g, const float *vol, float *sino, int a_begin, int a_end, float *vn, float *vt,
+                         cudaStream_t st);
+static int run_bp_mirror(const wt_geom *g, const float *sino, float *vol, int a_begin, int a_end, float scale, float *sp,
+                         cudaStream_t st);
 
 int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angle_begin, int angle_end, void *ws,
           size_t ws_bytes, void *stream) {
@@ -309,13 +315,46 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angl
     if (nimages <= 0) return invalid("wt_fp: nimages must be positive");
     if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_fp: bad angle range");
     if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_fp: workspace too small"; return WT_ERR_WORKSPACE; }
+    const int npack = nimages == 1 ? 2 : nimages;   // a single image is packed as a mirror pair
     Carver cv(ws, ws_bytes);
-    float *vn = cv.take<float>(vn_floats(g, nimages));
-    float *vt = cv.take<float>(vt_floats(g, nimages));
+    float *vn = cv.take<float>(vn_floats(g, npack));
+    float *vt = cv.take<float>(vt_floats(g, npack));
+    if (nimages == 1) return run_fp_mirror(g, vol, sino, angle_begin, angle_end, vn, vt, (cudaStream_t)stream);
     HFpStore epi;
     epi.sino = sino;
     epi.plane = (size_t)g->nangles * g->ndet;
     return run_fp(g, vol, nimages, angle_begin, angle_end, vn, vt, epi, (cudaStream_t)stream);
+}
+
+// single image, plain store: mirror pairing through the V = 2 kernels (DESIGN.md "Single-image problems")
+static int run_fp_mirror(const wt_geom *g, const float *vol, float *sino, int a_begin, int a_end, float *vn, float *vt,
+                         cudaStream_t st) {
+    FpParams p;
+    p.vn = vn; p.vt = vt; p.ang = g->d_fp;
+    p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
+    p.R = g->rows; p.C = g->cols; p.D = (g->ndet + 1) / 2; p.A = g->nangles;
+    p.a_begin = a_begin; p.a_end = a_end;
+    FpEpiStoreMirror epi;
+    epi.sino = sino; epi.Dfull = g->ndet;
+    launch_pack_vol<2, true>(vol, vn, vt, g->rows, g->cols, 1, st);
+    WT_CUDA(launch_fp<2>(p, epi, 1, st));
+    WT_CUDA(cudaGetLastError());
+    return WT_OK;
+}
+
+static int run_bp_mirror(const wt_geom *g, const float *sino, float *vol, int a_begin, int a_end, float scale, float *sp,
+                         cudaStream_t st) {
+    BpParams p;
+    p.sp = sp; p.ang = g->d_bp;
+    p.R = (g->rows + 1) / 2; p.C = g->cols; p.A = g->nangles;
+    p.padl = g->sino_padl; p.pitch = g->sino_pitch;
+    p.a_begin = a_begin; p.a_end = a_end;
+    BpEpiStoreMirror epi;
+    epi.vol = vol; epi.scale = scale; epi.Rfull = g->rows;
+    launch_pack_sino<2, true>(sino, sp, g, 1, st);
+    WT_CUDA(launch_bp<2>(p, epi, 1, st));
+    WT_CUDA(cudaGetLastError());
+    return WT_OK;
 }
 
 int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned char *mask, const float *inv_ngood,
@@ -353,8 +392,10 @@ int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angl
     if (nimages <= 0) return invalid("wt_bp: nimages must be positive");
     if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_bp: bad angle range");
     if (ws_bytes < wt_workspace_bytes(g, nimages)) { g_err = "wt_bp: workspace too small"; return WT_ERR_WORKSPACE; }
+    const int npack = nimages == 1 ? 2 : nimages;   // a single image is packed as a mirror pair
     Carver cv(ws, ws_bytes);
-    float *sp = cv.take<float>((size_t)nimages * g->nangles * g->sino_pitch);
+    float *sp = cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);
+    if (nimages == 1) return run_bp_mirror(g, sino, vol, angle_begin, angle_end, scale, sp, (cudaStream_t)stream);
     HBpStore epi;
     epi.vol = vol;
     epi.scale = scale;

@@ -16,9 +16,11 @@
 namespace wt {
 
 // ---- packing: plain (n, A, D) -> SP (G, A, pitch, V) with `padl` zero detectors in front ------------
-template <int V>
+// MIRROR (V == 2, one image): component 1 is the detector-reversed row q[a][D-1-d] (see BpEpiStoreMirror)
+template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict__ sino, float *__restrict__ sp, int A,
                                                         int D, int padl, int pitch) {
+    static_assert(!MIRROR || V == 2, "mirror pairing packs one image as two components");
     typedef typename VecOf<V>::T VecT;
     const int g = blockIdx.z, a = blockIdx.y;
     const size_t plane = (size_t)A * D;
@@ -26,16 +28,18 @@ __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict_
         const int d = dp - padl;
         float v[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i)
-            v[i] = (d >= 0 && d < D) ? __ldg(sino + ((size_t)g * V + i) * plane + (size_t)a * D + d) : 0.0f;
+        for (int i = 0; i < V; ++i) {
+            if (MIRROR) v[i] = (d >= 0 && d < D) ? __ldg(sino + (size_t)g * plane + (size_t)a * D + (i ? D - 1 - d : d)) : 0.0f;
+            else v[i] = (d >= 0 && d < D) ? __ldg(sino + ((size_t)g * V + i) * plane + (size_t)a * D + d) : 0.0f;
+        }
         reinterpret_cast<VecT *>(sp)[((size_t)g * A + a) * pitch + dp] = pack<V>(v);
     }
 }
 
-template <int V>
+template <int V, bool MIRROR = false>
 inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, cudaStream_t st) {
     dim3 grid((g->sino_pitch + 255) / 256, g->nangles, groups);
-    pack_sino_kernel<V><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch);
+    pack_sino_kernel<V, MIRROR><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch);
 }
 
 struct BpParams {
@@ -56,6 +60,23 @@ struct BpEpiStore {
         const size_t img = (size_t)p.R * p.C;
 #pragma unroll
         for (int i = 0; i < V; ++i) vol[((size_t)g * V + i) * img + (size_t)row * p.C + col] = scale * val[i];
+    }
+};
+
+// single image through the V = 2 kernel (mirror pairing): launched with p.R = ceil(R/2); component 0 is pixel
+// (row, col), component 1 its point reflection (R-1-row, C-1-col), whose detector coordinate is (D-1) - d*.
+struct BpEpiStoreMirror {
+    float *vol;   // (n, Rfull, C), one image per group
+    float scale;
+    int Rfull;
+    template <int V>
+    __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col,
+                                               const float (&val)[V]) const {
+        static_assert(V == 2, "mirror pairing is a V = 2 launch");
+        float *img = vol + (size_t)g * Rfull * p.C;
+        img[(size_t)row * p.C + col] = scale * val[0];
+        const int mr = Rfull - 1 - row;
+        if (mr != row) img[(size_t)mr * p.C + (p.C - 1 - col)] = scale * val[1];
     }
 };
 

@@ -114,6 +114,8 @@ class Projector(object):
         if out is None:
             alloc = torch.empty if angle_range is None else torch.zeros
             out = alloc((n,) + self.sino_shape, dtype=torch.float32, device=self.device)
+        if n == 0:                                   # empty batch: nothing to launch
+            return out.reshape(lead + self.sino_shape)
         nbytes = self.lib.wt_workspace_bytes(self.handle, n)
         ws = self._workspace(nbytes)
         _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
@@ -126,6 +128,8 @@ class Projector(object):
         if out is None:
             out = torch.empty((n,) + self.vol_shape, dtype=torch.float32, device=self.device)
         a0, a1 = (0, self.nangles) if angle_range is None else angle_range
+        if n == 0:
+            return out.reshape(lead + self.vol_shape)
         nbytes = self.lib.wt_workspace_bytes(self.handle, n)
         ws = self._workspace(nbytes)
         _capi.check(self.lib.wt_bp(self.handle, _ptr(s), _ptr(out), n, int(a0), int(a1), float(scale), _ptr(ws), nbytes,
