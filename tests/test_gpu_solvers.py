@@ -220,3 +220,28 @@ def test_stack_reconstruction_in_resident_batches(golden):
         assert (s0, s1) == ((0, 4), (4, 7))[rank]
         parts.append(out)
     assert torch.equal(torch.cat(parts), whole.cpu())
+
+
+def test_white_projection_real_data_branch():
+    """angles + sinogram given (src/white_projection.py:35-36,48-58): D = sinogram width, volume side int((D-1)/sqrt 2),
+    the caller's sinogram is normalised by the source integral (on a copy, B2)"""
+    from whitomo_b200.white_projection import WhiteProjection
+    ang = np.deg2rad(np.arange(0, 200, 0.5))[::8]                    # teeth_recon/teeth_io.py:52 style sampling
+    D = 91
+    rng = np.random.default_rng(2)
+    sino = rng.uniform(0.2, 1.0, (ang.shape[0], D))
+    keep = sino.copy()
+    grid = np.array([[2.5, 10], [0.005, 0.005]]).T
+    wp = WhiteProjection(source=np.array([2.0, 1.0]), pixel_size=1e-5, element_numbers=np.array([301, 302]),
+                         element_absorptions=np.array([[4000, 302.0], [300, 2000]]), energy_grid=grid, ph_size=None,
+                         sinogram=sino, angles=ang)
+    w = int((D - 1) / np.sqrt(2))
+    assert wp.ph_size == (w, w) and wp.proj_shape == (ang.shape[0], D) and wp.conc_shape == (2, w, w)
+    assert np.array_equal(sino, keep)                                 # not modified in place
+    assert np.allclose(wp.sinogram, keep.ravel() / np.sum(np.array([2.0, 1.0]) * grid[:, 1]))
+    c = rng.uniform(0.05, 0.2, wp.conc_shape)
+    g_geom = oracle.Geometry(w, w, D, ang)
+    wo = ow.WhiteOracle(np.array([2.0, 1.0]), 1e-5, np.array([[4000, 302.0], [300, 2000]]), grid, (w, w), geometry=g_geom)
+    wo.sinogram = wp.sinogram
+    assert abs(wp.func(c) - wo.func(c)) < 1e-4 * wo.func(c)
+    assert rel_l2(wp.grad(c), wo.grad(c)) < 5e-4

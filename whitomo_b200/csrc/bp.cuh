@@ -212,11 +212,13 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 template <int V, class Epi>
 inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
     const size_t smem = sizeof(BpSmem<V>);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.R + BP_TH - 1) / BP_TH, groups);
     bp_kernel<V, Epi><<<grid, BP_BLOCK, smem, st>>>(p, epi);

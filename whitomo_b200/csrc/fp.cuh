@@ -318,11 +318,13 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
 template <int V, class Epi>
 inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
     const size_t smem = sizeof(FpSmem<V>);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((p.D + FP_DT - 1) / FP_DT, p.ntiles, groups);
     fp_kernel<V, Epi><<<grid, FP_BLOCK, smem, st>>>(p, epi);

@@ -24,6 +24,19 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_own_device(method):
+    """run a Projector method with the projector's device current (streams and launches are per device)"""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class Spectrum(object):
     """Device tables of the polychromatic model (constructor state of WhiteProjection,
     src/white_projection.py:23-73).  ``source`` must already be normalised by its integral."""
@@ -105,6 +118,7 @@ class Projector(object):
         return t.reshape((-1,) + tuple(shape)).contiguous(), lead
 
     # ---- operators ------------------------------------------------------------------------------
+    @_on_own_device
     def fp(self, vol, out=None, angle_range=None):
         """p = W x.  vol (..., rows, cols) -> (..., nangles, ndet) float32 on the device.  With angle_range only
         those sinogram rows are computed (the others are zero in a fresh output)."""
@@ -121,6 +135,7 @@ class Projector(object):
         _capi.check(self.lib.wt_fp(self.handle, _ptr(v), _ptr(out), n, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
         return out.reshape(lead + self.sino_shape)
 
+    @_on_own_device
     def bp(self, sino, out=None, angle_range=None, scale=1.0):
         """g = scale * W^T q (exact transpose).  sino (..., nangles, ndet) -> (..., rows, cols)."""
         s, lead = self._as_images(sino, self.sino_shape)
@@ -136,6 +151,7 @@ class Projector(object):
                                    _stream()))
         return out.reshape(lead + self.vol_shape)
 
+    @_on_own_device
     def sirt(self, sino, n_iters=100):
         """ASTRA-style SIRT from x0 = 0; sino (..., nangles, ndet) -> (..., rows, cols)."""
         s, lead = self._as_images(sino, self.sino_shape)
@@ -146,6 +162,7 @@ class Projector(object):
         _capi.check(self.lib.wt_sirt(self.handle, _ptr(s), _ptr(out), n, int(n_iters), _ptr(ws), nbytes, _stream()))
         return out.reshape(lead + self.vol_shape)
 
+    @_on_own_device
     def ramp_filter(self, sino):
         """Fourier ramp of ASTRA's CPU FBP: zero-pad to pow2 >= 2D, multiply bin i by 2 i / zp."""
         s, lead = self._as_images(sino, self.sino_shape)
@@ -161,6 +178,7 @@ class Projector(object):
         """x = pi/(2A) * W^T ramp(p)  (cpu_fbp, src/astra_proxy.py:87-102)."""
         return self.bp(self.ramp_filter(sino), scale=np.pi / (2.0 * self.nangles))
 
+    @_on_own_device
     def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True,
                  angle_range=None):
         """Fused white-beam forward model + residual (wt_white_fp).  conc (S, K, rows, cols) or (K, rows, cols).
@@ -186,6 +204,7 @@ class Projector(object):
                                          _ptr(loss), S, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
         return inten, qmu, loss
 
+    @_on_own_device
     def mar_fp(self, vol, b, mask, inv_ngood, bt, b_hb, want_u=True, want_proj=False, want_stats=True):
         """Fused mono-MAR residual (wt_mar_fp).  vol (n, R, C); b (n, A, D); mask (n, A, D) uint8; inv_ngood (n,).
         Returns (u | None, proj | None, stats (n, 3) float64 | None): cost, hough phi sum, #infeasible metal rays."""
@@ -203,6 +222,7 @@ class Projector(object):
                                        _ptr(u), _ptr(pr), _ptr(st), n, _ptr(ws), nbytes, _stream()))
         return u, pr, st
 
+    @_on_own_device
     def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, triv_w=0.0, lower_only=False,
                        mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None, want_penalty=False):
         """In-place fused K3 step (wt_barrier_update).  x, grad: (S, K, rows, cols) / (K, rows, cols) / (rows, cols)."""
