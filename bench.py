@@ -193,6 +193,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from whitomo_b200.distributed import bind_to_gpu_numa_node
+    numa_bound = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -342,7 +344,8 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "slices_per_gpu_per_step": S, "images_per_step": S * K * world,
                    "l2": "inputs larger than L2 (%.0f MB of concentrations + %.0f MB of q*mu per step per GPU)"
                          % (4e-6 * S * K * N * N, 4e-6 * S * K * A * D),
-                   "parallelism": "slices sharded over %d rank(s), no data-path collective" % world},
+                   "parallelism": "slices sharded over %d rank(s), no data-path collective" % world,
+                   "cpu_affinity": "NVML ideal CPU set of the rank's GPU" if numa_bound else "default"},
         "barrier_iters_per_s": S * world * args.steps / elapsed,
         "fp_gups": K * N * N * A * S / t_fp / 1e9, "bp_gups": K * N * N * A * S / t_bp / 1e9,
         "kernel_ms": {"white_fp": t_fp * 1e3, "bp": t_bp * 1e3, "barrier_update": t_up * 1e3},

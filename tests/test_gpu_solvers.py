@@ -245,3 +245,14 @@ def test_white_projection_real_data_branch():
     wo.sinogram = wp.sinogram
     assert abs(wp.func(c) - wo.func(c)) < 1e-4 * wo.func(c)
     assert rel_l2(wp.grad(c), wo.grad(c)) < 5e-4
+
+
+def test_example_script_reference_style_equals_fused():
+    """examples/barrier_gogo.py: the reference's call pattern (numpy closures + barrier_method) and the fused device
+    loop reconstruct the same concentrations"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "barrier_gogo.py"), "64", "60"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "relative L2 between the two reconstructions" in r.stdout

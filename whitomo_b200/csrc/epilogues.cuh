@@ -265,9 +265,12 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
             if (f.use_triv) rg += prm.triv_w * (v * (v * (4.0f * v - 3.0f) + 1.0f));
             gt += prm.beta_reg * rg;
             if (f.use_bar) {
-                // -1/x + 1/(1-x) = (2x - 1) / (x (1 - x)): one reciprocal; +-inf on the faces like the reference
+                // grad phi = -g/f per constraint (src/barrier_method.py:50): -1/x for f = -x, -1/(x-1) for f = x-1;
+                // together (1 - 2x) / (x (x - 1)): one reciprocal.  The signs of the zeros are the reference's: on
+                // either face the quotient is -inf (x = 0: 1/(-0), x = 1: -1/(+0)), so a pixel clipped onto a face
+                // is thrown to +inf and clipped to 1, exactly like the numpy code.
                 if (f.lower_only) gt += f.bt * __fdividef(-1.0f, v);
-                else gt += f.bt * __fdividef(2.0f * v - 1.0f, v * (1.0f - v));
+                else gt += f.bt * __fdividef(1.0f - 2.0f * v, v * (v - 1.0f));
             }
             v = v - prm.alpha * gt;
         }

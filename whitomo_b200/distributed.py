@@ -65,3 +65,16 @@ class AngleSplit(object):
     def gather_sinogram(self, y_local):
         """full sinogram on every rank from the locally owned rows (rows outside the range must be zero)"""
         return self._allreduce(y_local.clone())
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs closest to its GPU (NVML's ideal affinity) so that pinned staging
+    buffers are first-touched on the GPU's own NUMA node: with 8 ranks per box every rank otherwise contends for
+    one socket's memory controllers during H2D/D2H.  Best effort: returns False if NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device_index))
+        return True
+    except Exception:
+        return False
