@@ -256,3 +256,53 @@ def test_example_script_reference_style_equals_fused():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "relative L2 between the two reconstructions" in r.stdout
+
+
+def test_masked_least_squares_scipy_cg_over_the_drop_in_and_device_cgls():
+    """teeth_recon/experiments.py:366-401: the reference's fmin_cg call runs unchanged over gpu_fp/gpu_bp and follows
+    the same path as over the oracle; the device CGLS reaches the same minimum of the same functional."""
+    import scipy.optimize as opt
+    from whitomo_b200 import astra_proxy as ap, solvers
+    n, na = 32, 40
+    pg = ap.astra.create_proj_geom('parallel', 1.0, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    vg = ap.astra.create_vol_geom(n, n)
+    pid = ap.astra.create_projector('linear', pg, vg)
+    g = oracle.Geometry.standard(n, na)
+    z_ph = np.zeros((n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    z_ph[(xx - 15.5) ** 2 + (yy - 15.5) ** 2 <= 144] = 0.10358164
+    z_ph[(xx - 18) ** 2 + (yy - 12) ** 2 <= 9] = 9.21754054
+    rng = np.random.RandomState(12345)
+    i0, bound = 1e9, 8.0
+    pr = rng.poisson(lam=np.exp(np.log(i0) - oracle.fp(g, z_ph).astype(np.float64)).flatten()).astype('float32').reshape(g.sino_shape)
+    r, m = ob.ray_transform_from_projection(pr.copy(), bound, i0)
+    b, mf = r.flatten(), m.flatten()
+
+    def closures(FP, BP):
+        def cost(x):
+            d = FP(x) - b
+            d[mf] = 0.0
+            return np.sum(d ** 2)
+
+        def grad(x):
+            d = FP(x) - b
+            d[mf] = 0.0
+            return 2.0 * BP(d)
+        return cost, grad
+
+    dev_c = closures(lambda x: ap.gpu_fp(pg, vg, x.reshape(n, n), pid).flatten(),
+                     lambda x: ap.gpu_bp(pg, vg, x.reshape(g.sino_shape), pid).flatten())
+    cpu_c = closures(lambda x: oracle.fp(g, x.reshape(n, n)).flatten(),
+                     lambda x: oracle.bp(g, x.reshape(g.sino_shape)).flatten())
+    x0 = np.zeros(n * n, dtype='float32')
+    xd = opt.fmin_cg(dev_c[0], x0, dev_c[1], maxiter=8, disp=False)
+    xc = opt.fmin_cg(cpu_c[0], x0, cpu_c[1], maxiter=8, disp=False)
+    assert rel_l2(xd, xc) < 5e-3          # the line search amplifies the fp32-level operator differences
+    assert abs(dev_c[0](xd) - cpu_c[0](xc)) < 1e-2 * cpu_c[0](xc)
+    assert dev_c[0](xd) < 0.05 * dev_c[0](x0.astype(np.float64))
+    # device CGLS: monotone cost, and after 200 iterations at least as low as 60 fmin_cg iterations on the CPU
+    P = ap.astra.projector_for(pg, vg, pid)
+    xs, costs = solvers.mask_linear_least_squares(P, pr.copy(), i0, bound, n_iters=200)
+    assert all(c1 <= c0 * (1 + 1e-4) for c0, c1 in zip(costs, costs[1:]))
+    x60 = opt.fmin_cg(cpu_c[0], x0, cpu_c[1], maxiter=60, disp=False)
+    assert cpu_c[0](xs.cpu().numpy().flatten().astype(np.float64)) <= 1.05 * cpu_c[0](x60)

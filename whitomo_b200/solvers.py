@@ -242,3 +242,36 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
         out[b0 - s0:b1 - s0].copy_(res, non_blocking=True)
     torch.cuda.synchronize(dev)
     return out, (s0, s1)
+
+
+def mask_linear_least_squares(proj, pr, i0, bound, n_iters=200, x0=None):
+    """Masked least squares of teeth_recon/experiments.py:366-401:  min_x || M (W x - r) ||^2, M = good rays.
+
+    The reference hands (cost, grad = 2 W^T M (W x - r)) to scipy.optimize.fmin_cg (non-linear CG with a line
+    search: 2-3 FP per iteration); that call keeps working unchanged over the drop-in gpu_fp / gpu_bp.  The
+    objective is quadratic, so this device version runs linear CG on the normal equations W^T M W x = W^T M r
+    (CGLS): exactly one FP and one BP per iteration, dot products on the device.  Both minimise the same
+    functional; iterates differ, minimisers agree.  Returns (x, cost per iteration)."""
+    dev = proj.device
+    p = torch.as_tensor(np.asarray(pr) if not isinstance(pr, torch.Tensor) else pr).to(dev, dtype=torch.float32).clone()
+    r, m = ray_transform_from_projection(p.reshape(proj.sino_shape), bound, i0)
+    good = (~m).to(torch.float32)
+    x = torch.zeros(proj.vol_shape, dtype=torch.float32, device=dev) if x0 is None else x0.to(dev).float().clone()
+    res = good * (r - proj.fp(x))                  # M (r - W x)
+    s = proj.bp(res)                               # W^T M (r - W x) = -grad/2
+    d = s.clone()
+    gamma = torch.sum(s.double() * s.double())
+    costs = []
+    for _ in range(n_iters):
+        costs.append(torch.sum(res.double() ** 2).item())
+        if gamma.item() == 0.0:
+            break
+        q = good * proj.fp(d)
+        step = gamma / torch.sum(q.double() * q.double())
+        x += step.float() * d
+        res -= step.float() * q
+        s = proj.bp(res)
+        gamma_new = torch.sum(s.double() * s.double())
+        d = s + (gamma_new / gamma).float() * d
+        gamma = gamma_new
+    return x, costs
