@@ -356,9 +356,10 @@ def run_gpu(args):
                          % (100 * t_fp / (t_fp + t_bp + t_up)),
                          note="gather/stencil kernel with ~N-fold on-chip reuse: bound by shared-memory load bandwidth "
                               "(see `onchip`), not HBM (SURVEY 8d: compulsory-bytes ceiling of the HBM fraction is ~0.4%); "
-                              "DRAM traffic is ~12x the algorithmic bytes because a float4 group's packed volume copy "
-                              "(67 MB) is re-swept by every wave of CTAs past the effective L2 share -- 0.32 TB/s, 4% of "
-                              "DRAM bandwidth, off the critical path"),
+                              "DRAM traffic stays a few times the algorithmic bytes because a float4 group's packed volume "
+                              "copy (67 MB) exceeds the effective L2 share and every wave of CTAs sweeps it (alternating "
+                              "the sweep direction per wave cut it 2.5x) -- ~0.13 TB/s, 2% of DRAM bandwidth, off the "
+                              "critical path"),
         "roofline_bp": dict(roof(bp_bytes, t_bp, "bp"), kernel="bp_kernel<4> (TMA-staged gather)"),
         "roofline_update": dict(roof(up_bytes, t_up, "update"), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3)"),
         "e2e": {"value": upd_per_step * args.steps / e2e_elapsed / 1e9, "unit": UNIT,

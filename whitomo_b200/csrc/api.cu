@@ -60,6 +60,12 @@ static std::vector<Chunk> chunks(int n, int multiple_of = 1) {
     return c;
 }
 
+static int sweep_tiles() {
+    static int v = 0;
+    if (!v) { const char *e = getenv("WT_FP_SWEEP_TILES"); v = e ? atoi(e) : FP_SWEEP_TILES; if (v < 1) v = 1; }
+    return v;
+}
+
 template <int V, class Epi>
 static cudaError_t fp_chunk(const FpParams &p, const Epi &epi, const float *src, float *vn, float *vt, int groups,
                             cudaStream_t st) {
@@ -79,7 +85,7 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
         p.vn = vn; p.vt = vt; p.ang = g->d_fp;
         p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
         p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
-        p.a_begin = a_begin; p.a_end = a_end;
+        p.a_begin = a_begin; p.a_end = a_end; p.sweep_tiles = sweep_tiles();
         const float *src = vol + (size_t)c.first * img;
         Epi epi = epi_proto.offset(c.first);
         switch (c.v) {
@@ -333,7 +339,7 @@ static int run_fp_mirror(const wt_geom *g, const float *vol, float *sino, int a_
     p.vn = vn; p.vt = vt; p.ang = g->d_fp;
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
     p.R = g->rows; p.C = g->cols; p.D = (g->ndet + 1) / 2; p.A = g->nangles;
-    p.a_begin = a_begin; p.a_end = a_end;
+    p.a_begin = a_begin; p.a_end = a_end; p.sweep_tiles = sweep_tiles();
     FpEpiStoreMirror epi;
     epi.sino = sino; epi.Dfull = g->ndet;
     launch_pack_vol<2, true>(vol, vn, vt, g->rows, g->cols, 1, st);

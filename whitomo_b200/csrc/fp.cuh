@@ -28,6 +28,7 @@ constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only driv
 constexpr int FP_LB = 16;       // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
 constexpr int FP_STAGES = 4;
+constexpr int FP_SWEEP_TILES = 4;  // angle tiles per sweep direction (~ one wave of 148 x 2 resident CTAs; measured: 1,2,3,4,6,8 -> 1.80, 1.29, 0.98, 0.81, 1.08, 1.31 GB)
 // budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
 // for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
 constexpr int FP_WFIT = FP_W - 8;
@@ -105,6 +106,7 @@ struct FpParams {
     int ntiles;
     int R, C, D, A;
     int a_begin, a_end;
+    int sweep_tiles;   // angle tiles per sweep direction (FP_SWEEP_TILES)
 };
 
 // plain store: sino (n, A, D)
@@ -235,10 +237,16 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const bool tile_in_range = tile.first < p.a_end && tile.first + tile.count > p.a_begin;   // CTA-uniform
     const int nchunk = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
 
-    // producer warp: stage chunk `ch` = lines [Lb + ch*LB, +LB)
+    // Sweep direction alternates every FP_SWEEP_TILES angle tiles (about one wave of resident CTAs): a float4 group's
+    // packed copy (67 MB at 2048^2) does not fit the effective L2 share, and same-direction sweeps of consecutive
+    // waves evict every line before its re-use (ncu: 16x the compulsory DRAM reads).  Sweeping back over the lines
+    // the previous wave touched last turns most of those misses into L2 hits.  A ray's sum order depends only on
+    // its tile index, so results stay deterministic and independent of batch composition and angle range.
+    const bool reverse = ((blockIdx.y / p.sweep_tiles) & 1) != 0;
+    // producer warp: stage chunk `ch` = the ch-th chunk of FP_LB lines in sweep order
     auto produce = [&](int ch) {
         const int s = ch % FP_STAGES;
-        const int l0 = Lb + ch * FP_LB;
+        const int l0 = Lb + (reverse ? nchunk - 1 - ch : ch) * FP_LB;
         const int l1 = min(l0 + FP_LB, nlines) - 1;
         // left-most position any ray of the tile takes on these lines (linear in l: attained at an end)
         float m = 3.0e38f;
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         for (int ch = 0; ch < nchunk; ++ch) {
             const int s = ch % FP_STAGES;
             mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
-            const int l0 = Lb + ch * FP_LB;
+            const int l0 = Lb + (reverse ? nchunk - 1 - ch : ch) * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
             if (la < lb) {
                 // c - 0.5 relative to the window start at line la; then one FADD per line
