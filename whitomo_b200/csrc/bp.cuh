@@ -16,12 +16,14 @@
 namespace wt {
 
 // ---- packing: plain (n, A, D) -> SP (G, A, pitch, V) with `padl` zero detectors in front ------------
-// MIRROR (V == 2, one image): component 1 is the detector-reversed row q[a][D-1-d] (see BpEpiStoreMirror)
+// MIRROR: the group holds V0 = V/2 images; components [V0, V) are the detector-reversed rows q[a][D-1-d]
+// (pixel (R-1-row, C-1-col) sees detector coordinate (D-1) - d*, see the kernel's epilogue)
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict__ sino, float *__restrict__ sp, int A,
                                                         int D, int padl, int pitch) {
-    static_assert(!MIRROR || V == 2, "mirror pairing packs one image as two components");
+    static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
+    constexpr int V0 = MIRROR ? V / 2 : V;
     const int g = blockIdx.z, a = blockIdx.y;
     const size_t plane = (size_t)A * D;
     for (int dp = blockIdx.x * blockDim.x + threadIdx.x; dp < pitch; dp += gridDim.x * blockDim.x) {
@@ -29,8 +31,9 @@ __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict_
         float v[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (MIRROR) v[i] = (d >= 0 && d < D) ? __ldg(sino + (size_t)g * plane + (size_t)a * D + (i ? D - 1 - d : d)) : 0.0f;
-            else v[i] = (d >= 0 && d < D) ? __ldg(sino + ((size_t)g * V + i) * plane + (size_t)a * D + d) : 0.0f;
+            const bool rev = MIRROR && i >= V0;
+            const size_t im = (size_t)g * V0 + (rev ? i - V0 : i);
+            v[i] = (d >= 0 && d < D) ? __ldg(sino + im * plane + (size_t)a * D + (rev ? D - 1 - d : d)) : 0.0f;
         }
         reinterpret_cast<VecT *>(sp)[((size_t)g * A + a) * pitch + dp] = pack<V>(v);
     }
@@ -46,6 +49,7 @@ struct BpParams {
     const float *sp;  // packed sinogram (G, A, pitch, V)
     const BpAngle *ang;
     int R, C, A;
+    int Rproc;        // rows that get a thread: R, or ceil(R/2) under mirror pairing
     int padl, pitch;
     int a_begin, a_end;
 };
@@ -63,23 +67,6 @@ struct BpEpiStore {
     }
 };
 
-// single image through the V = 2 kernel (mirror pairing): launched with p.R = ceil(R/2); component 0 is pixel
-// (row, col), component 1 its point reflection (R-1-row, C-1-col), whose detector coordinate is (D-1) - d*.
-struct BpEpiStoreMirror {
-    float *vol;   // (n, Rfull, C), one image per group
-    float scale;
-    int Rfull;
-    template <int V>
-    __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col,
-                                               const float (&val)[V]) const {
-        static_assert(V == 2, "mirror pairing is a V = 2 launch");
-        float *img = vol + (size_t)g * Rfull * p.C;
-        img[(size_t)row * p.C + col] = scale * val[0];
-        const int mr = Rfull - 1 - row;
-        if (mr != row) img[(size_t)mr * p.C + (p.C - 1 - col)] = scale * val[1];
-    }
-};
-
 template <int V>
 struct BpSmem {
     typedef typename VecOf<V>::T VecT;
@@ -90,7 +77,9 @@ struct BpSmem {
     uint64_t empty[BP_STAGES];  // all consumer warps are done reading a stage
 };
 
-template <int V, class Epi>
+// Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
+// MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
+template <int V, class Epi, bool MIRROR>
 __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -98,7 +87,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 
     const int g = blockIdx.z;
     const int col0 = blockIdx.x * BP_TW, row0 = blockIdx.y * BP_TH;
-    const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.R - row0);  // real pixels of this tile
+    const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.Rproc - row0);  // real pixels of this tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nblk = (p.a_end - p.a_begin + BP_AB - 1) / BP_AB;
 
@@ -204,24 +193,36 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int col = col0 + lane + 32 * c;
-            if (row < p.R && col < p.C) epi.template operator()<V>(p, g, row, col, acc[r][c]);
+            if (row < p.Rproc && col < p.C) {
+                if constexpr (MIRROR) {
+                    constexpr int W = V / 2;
+                    float direct[W], mirrored[W];
+#pragma unroll
+                    for (int i = 0; i < W; ++i) { direct[i] = acc[r][c][i]; mirrored[i] = acc[r][c][W + i]; }
+                    epi.template operator()<W>(p, g, row, col, direct);
+                    const int mr = p.R - 1 - row;     // the middle row of an odd-height image is its own mirror row
+                    if (mr != row) epi.template operator()<W>(p, g, mr, p.C - 1 - col, mirrored);
+                } else {
+                    epi.template operator()<V>(p, g, row, col, acc[r][c]);
+                }
+            }
         }
     }
 }
 
-template <int V, class Epi>
+template <int V, class Epi, bool MIRROR = false>
 inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
     const size_t smem = sizeof(BpSmem<V>);
     static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.R + BP_TH - 1) / BP_TH, groups);
-    bp_kernel<V, Epi><<<grid, BP_BLOCK, smem, st>>>(p, epi);
+    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.Rproc + BP_TH - 1) / BP_TH, groups);
+    bp_kernel<V, Epi, MIRROR><<<grid, BP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
 }
 

@@ -13,7 +13,7 @@ struct FpEpiSirtResidual {
     float *out;           // (n, A, D)
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *) const {
+                                               const float (&val)[V], float *, int, int) const {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const float rs = __ldg(raysum + r);
@@ -58,12 +58,13 @@ struct FpEpiWhite {
     float *partial;     // (S, nblocks) per-CTA sums of q^2, or null
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *scratch) const {
+                                               const float (&val)[V], float *scratch, int pass, int npass) const {
         static_assert(V % K == 0, "group must hold whole slices");
         constexpr int SPG = V / K;
         __shared__ float red[SPG][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
-        const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const int nblocks = gridDim.x * gridDim.y * npass;
+        const int bid = pass * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.x;
         // spectrum tables -> shared memory (the projector's staging buffers are idle now): broadcast LDS in the bin loop
         const int ntab = (K + 1) * E;
@@ -127,11 +128,13 @@ struct FpEpiMar {
     int nimg;                    // n of this launch (stride of the partial planes)
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *) const {
+                                               const float (&val)[V], float *, int pass, int npass) const {
         __shared__ float red[3][V][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
-        const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const int nblocks = gridDim.x * gridDim.y * npass;
+        const int bid = pass * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
         const int tid = threadIdx.x;
+        if (partial) __syncthreads();   // a previous pass may still be reading `red`
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const size_t im = (size_t)g * V + i;

@@ -41,21 +41,22 @@ __host__ __device__ inline int fp_pitch(int npos) {
 
 // ---- packing: plain (n, R, C) -> VN (G, R, pitch(C), V) and VT (G, C, pitch(R), V), zero padded -------
 // position k of a line lives at slot k + VPAD; everything else in the line is zero.
-// MIRROR (V == 2, one image): component 1 is the point reflection x[R-1-r][C-1-c] of the image.  A parallel-beam ray
-// (a, d) through the reflected image is the ray (a, D-1-d) through the image, so a single image runs through the
-// V = 2 kernels with half the rays -- 6.5 instead of 11 instructions per update (see FpEpiStoreMirror).
+// MIRROR: the group holds V0 = V/2 images; components [V0, V) are their point reflections x[R-1-r][C-1-c].  A
+// parallel-beam ray (a, d) through the reflected image is the ray (a, D-1-d) through the image, so one or two images
+// run through the V = 2 / V = 4 kernels with half the rays and shared index arithmetic (DESIGN.md "mirror pairing").
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__ vol, float *__restrict__ vn,
                                                        float *__restrict__ vt, int R, int C) {
-    static_assert(!MIRROR || V == 2, "mirror pairing packs one image as two components");
+    static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
+    constexpr int V0 = MIRROR ? V / 2 : V;   // images per group
     __shared__ float tile[V][32][33];
     const int g = blockIdx.z;
     const int r0 = blockIdx.y * 32 - VPAD, c0 = blockIdx.x * 32 - VPAD;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int Cp = fp_pitch(C), Rp = fp_pitch(R);
     const size_t img = (size_t)R * C;
-    const float *src = vol + (size_t)g * (MIRROR ? 1 : V) * img;
+    const float *src = vol + (size_t)g * V0 * img;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int rr = ty + 8 * k;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
         const bool in = (r >= 0 && r < R && c >= 0 && c < C);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (MIRROR && i == 1) v[i] = in ? __ldg(src + (size_t)(R - 1 - r) * C + (C - 1 - c)) : 0.0f;
+            if (MIRROR && i >= V0) v[i] = in ? __ldg(src + (i - V0) * img + (size_t)(R - 1 - r) * C + (C - 1 - c)) : 0.0f;
             else v[i] = in ? __ldg(src + i * img + (size_t)r * C + c) : 0.0f;
             tile[i][rr][tx] = v[i];
         }
@@ -105,6 +106,7 @@ struct FpParams {
     const FpTile *tiles;
     int ntiles;
     int R, C, D, A;
+    int Dproc;         // detectors that get a thread: D, or ceil(D/2) under mirror pairing
     int a_begin, a_end;
     int sweep_tiles;   // angle tiles per sweep direction (FP_SWEEP_TILES)
 };
@@ -114,28 +116,11 @@ struct FpEpiStore {
     float *sino;
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *) const {
+                                               const float (&val)[V], float *, int, int) const {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D;
 #pragma unroll
         for (int i = 0; i < V; ++i) sino[((size_t)g * V + i) * plane + (size_t)a * p.D + d] = val[i];
-    }
-};
-
-// single image through the V = 2 kernel (mirror pairing): launched with p.D = ceil(D/2); component 0 is ray (a, d),
-// component 1 ray (a, D-1-d).  The per-angle constants are centro-symmetric up to float32 rounding (~1e-4 position),
-// so the mirrored ray differs from its direct evaluation at rounding level only.
-struct FpEpiStoreMirror {
-    float *sino;   // (n, A, Dfull), one image per group
-    int Dfull;
-    template <int V>
-    __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *) const {
-        static_assert(V == 2, "mirror pairing is a V = 2 launch");
-        if (!valid) return;
-        float *row = sino + ((size_t)g * p.A + a) * Dfull;
-        row[d] = val[0];
-        if (Dfull - 1 - d != d) row[Dfull - 1 - d] = val[1];
     }
 };
 
@@ -150,7 +135,11 @@ struct FpSmem {
     int lo, hi;                                    // line range any ray of the CTA needs
 };
 
-template <int V, class Epi>
+// Epilogue contract: epi.operator()<W>(p, g, a, d, valid, val[W], cta_scratch, pass, npass) handles the W images of
+// group g (image index g*W + i) for ray (a, d); it is called by ALL threads of the CTA (it may synchronise).  Under
+// MIRROR the V components are V/2 images x {ray (a, d), mirrored ray (a, D-1-d)}: the epilogue then runs twice with
+// W = V/2, pass = 0, 1 of npass = 2 (per-CTA partial sums are laid out per pass).
+template <int V, class Epi, bool MIRROR>
 __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -165,7 +154,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const int a = tile.first + slot;
     const int g = blockIdx.z;
     const bool producer = warp == FP_THREADS / 32;
-    const bool intile = !producer && (slot < tile.count) && (d < p.D);
+    const bool intile = !producer && (slot < tile.count) && (d < p.Dproc);
     const bool valid = intile && (a >= p.a_begin) && (a < p.a_end);   // angle-range calls skip the other rays
 
     // orientation is uniform over the tile
@@ -191,7 +180,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         const int aa = tile.first + tid;
         if (tid < tile.count) {
             const FpAngle an = p.ang[aa];
-            const int dl_ = min(d0 + FP_DT, p.D) - 1;
+            const int dl_ = min(d0 + FP_DT, p.Dproc) - 1;
             const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
             const double cb = an.c0_base + ((double)dl_ + 0.5) * an.c0_step;
             lo_c = (float)fmin(ca, cb);
@@ -316,26 +305,37 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         }
     }
 
-    float val[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) val[i] = acc[i] * len;
     // the staging buffers are free now: epilogues may use them as CTA scratch (after their own __syncthreads)
-    epi.template operator()<V>(p, g, a, d, valid, val, reinterpret_cast<float *>(&sm.seg[0][0][0]));
+    float *scratch = reinterpret_cast<float *>(&sm.seg[0][0][0]);
+    if constexpr (MIRROR) {
+        constexpr int W = V / 2;
+        float direct[W], mirrored[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) { direct[i] = acc[i] * len; mirrored[i] = acc[W + i] * len; }
+        const int dm = p.D - 1 - d;
+        epi.template operator()<W>(p, g, a, d, valid, direct, scratch, 0, 2);
+        epi.template operator()<W>(p, g, a, dm, valid && dm != d, mirrored, scratch, 1, 2);
+    } else {
+        float val[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) val[i] = acc[i] * len;
+        epi.template operator()<V>(p, g, a, d, valid, val, scratch, 0, 1);
+    }
 }
 
-template <int V, class Epi>
+template <int V, class Epi, bool MIRROR = false>
 inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
     const size_t smem = sizeof(FpSmem<V>);
     static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.D + FP_DT - 1) / FP_DT, p.ntiles, groups);
-    fp_kernel<V, Epi><<<grid, FP_BLOCK, smem, st>>>(p, epi);
+    dim3 grid((p.Dproc + FP_DT - 1) / FP_DT, p.ntiles, groups);
+    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
 }
 

@@ -222,8 +222,20 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
 
+    # Batches of fewer than 3 images would take the mirror-paired single-image path, whose results differ from the
+    # batched kernels at rounding level; keep every batch at >= 3 images where the range allows it, so that a
+    # slice's result does not depend on the batch size or on how the stack is sharded over ranks.
+    K = x0_host.shape[1]
+    min_slices = -(-3 // K)
+    cuts = list(range(s0, s1, batch)) + [s1]
+    if len(cuts) > 2 and cuts[-1] - cuts[-2] < min_slices:
+        cuts[-2] = max(cuts[-3] + min(min_slices, batch), cuts[-1] - min_slices) if batch > min_slices else cuts[-2]
+        if cuts[-1] - cuts[-2] < min_slices or cuts[-2] - cuts[-3] < min_slices:
+            del cuts[-2]                                     # merge the short tail into the previous batch
+    nxt_of = dict(zip(cuts[:-1], cuts[1:]))
+
     def upload(b0):
-        b1 = min(b0 + batch, s1)
+        b1 = nxt_of[b0]
         with torch.cuda.stream(copy_stream):
             m = meas_host[b0:b1].to(dev, non_blocking=True)
             x = x0_host[b0:b1].to(dev, non_blocking=True)
