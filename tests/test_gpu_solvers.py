@@ -306,3 +306,29 @@ def test_masked_least_squares_scipy_cg_over_the_drop_in_and_device_cgls():
     assert all(c1 <= c0 * (1 + 1e-4) for c0, c1 in zip(costs, costs[1:]))
     x60 = opt.fmin_cg(cpu_c[0], x0, cpu_c[1], maxiter=60, disp=False)
     assert cpu_c[0](xs.cpu().numpy().flatten().astype(np.float64)) <= 1.05 * cpu_c[0](x60)
+
+
+def test_active_set_compaction_is_bit_identical_and_saves_work(golden):
+    """slices that leave a barrier level early are dropped from the working set until the next level: same result
+    bit for bit as carrying them along masked, fewer slice-iterations spent"""
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    grid = z["grid"]
+    P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    sp = Spectrum(z["source"] / np.sum(z["source"] * grid[:, 1]), grid[:, 1], z["ea"], float(z["pixel_size"]))
+    rng = np.random.default_rng(11)
+    S = 6
+    gts = np.stack([np.clip(z["gt"] * s, 0, 1) for s in (1.0, 0.2, 0.9, 0.05, 0.6, 0.4)]).astype(np.float32)
+    meas = P.white_fp(sp, torch.from_numpy(gts).cuda(), want_qmu=False, want_loss=False)[0]
+    x0 = torch.from_numpy(np.stack([z["x0"] * rng.uniform(0.7, 1.3) for _ in range(S)]).astype(np.float32)).cuda()
+    p = dict(n_iter=12, n_biter=3, t0=0.1, t_step=0.5, alpha=0.3, ir_beta=0.05, max_iter=30,
+             n_steps_without_progress=2, min_delta_loss=0.5)
+    xa, ia = solvers.white_barrier_stack(P, sp, meas, x0, compact=True, **p)
+    xb, ib = solvers.white_barrier_stack(P, sp, meas, x0, compact=False, **p)
+    assert torch.equal(xa, xb) and torch.equal(ia["loss"], ib["loss"])
+    assert torch.equal(ia["slice_iters"], ib["slice_iters"])
+    spent = int(ia["slice_iters"].sum().item())
+    assert spent < ia["iters"] * S                      # some slices did stop early ...
+    assert len(set(ia["slice_iters"].tolist())) > 1     # ... at different times

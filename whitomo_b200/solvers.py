@@ -30,14 +30,19 @@ def _as_stack(x, K):
 
 def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1, t_step=0.5, alpha=1.0,
                         beta_reg=1.0, ir_beta=0.05, max_iter=5000, do_alpha_decay=True, min_delta_loss=1e-3,
-                        n_steps_without_progress=15, stat_cb=None, max_total_iters=None):
+                        n_steps_without_progress=15, stat_cb=None, max_total_iters=None, compact=True):
     """Log-barrier reconstruction of element concentrations 0 <= c <= 1 with the 0.05*|c0 c1| regulariser.
 
     Defaults are the reference's run (src/barrier_method_gogo.py:184-192).  ``meas`` (S, A, D) intensities,
-    ``x0`` (S, K, N, N) feasible start.  Returns (x, info) with info = dict(iters, loss (S,), trace list).
+    ``x0`` (S, K, N, N) feasible start.  Returns (x, info) with info = dict(iters, loss (S,), trace list,
+    slice_iters = projector iterations actually spent per slice).
     Per inner iteration and slice: one fused white-beam FP (K projections), K BP, one K3 launch.
     The loss of barrier_method's early-stop test at the new point is f(x') + penalty(x'); f(x') is the by-product
     of the FP that the next iteration's gradient needs anyway, so no projection is spent on statistics.
+    Early stop is per slice (each slice is its own barrier_method problem).  With ``compact`` the slices that left
+    a barrier level early are taken out of the working set until the next level, so no FP/BP is spent on them
+    (the working set never drops below 3 images, which keeps every slice on the batched kernels and its result
+    independent of what the other slices do).
     """
     K = spectrum.K
     x = _as_stack(x0, K)
@@ -51,38 +56,61 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
     t = float(t0)
     total = 0
     trace = []
+    slice_iters = torch.zeros(S, dtype=torch.int64, device=dev)
+    min_work = -(-3 // K)                            # slices that keep the working set at >= 3 images
     _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
+    done = False
     for i_biter in range(n_biter):
+        # working set of this barrier level: all slices; shrinks as slices stop early
+        idx = torch.arange(S, device=dev)
+        xw, mw, qw, fw = x, meas, qmu, f_loss
         prev = None
         stall = torch.zeros(S, dtype=torch.int32, device=dev)
         active = torch.ones(S, dtype=torch.bool, device=dev)
         for i_iter in range(n_iter):
-            g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+            n_w = xw.shape[0]
+            g = proj.bp(qw.reshape((n_w * K,) + proj.sino_shape), scale=-1.0)
             if stat_cb is not None:
-                stat_cb(dict(biter=i_biter, iter=i_iter, t=t, alpha=alpha, x=x, func=f_loss, grad=g))
-            pen = proj.barrier_update(x, g, alpha, beta_reg, t, reg_w=ir_beta, active=active,
+                stat_cb(dict(biter=i_biter, iter=i_iter, t=t, alpha=alpha, x=xw, slices=idx, func=fw, grad=g))
+            pen = proj.barrier_update(xw, g, alpha, beta_reg, t, reg_w=ir_beta, active=active,
                                       want_penalty=n_steps_without_progress is not None)
-            _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
+            _, qw, fw = proj.white_fp(spectrum, xw, meas=mw, want_intensity=False)
+            slice_iters[idx] += active.to(torch.int64)
             total += 1
             if n_steps_without_progress is not None:
-                loss = f_loss + pen
+                loss = fw + pen
                 if prev is not None:
                     progress = (prev - loss) >= min_delta_loss       # False for nan/inf, like the reference
                     stall = torch.where(active, torch.where(progress, torch.zeros_like(stall), stall + 1), stall)
                 prev = loss if prev is None else torch.where(active, loss, prev)
                 active = active & (stall < n_steps_without_progress)
-                trace.append(loss.detach())
-                if not bool(active.any()):
+                trace.append((idx, loss.detach()))
+                n_active = int(active.sum().item())
+                if n_active == 0:
                     break
+                if compact and n_active < n_w and n_active >= min_work:
+                    if xw is not x:
+                        x[idx], qmu[idx], f_loss[idx] = xw, qw, fw            # park what leaves the working set
+                    else:
+                        qmu, f_loss = qw, fw
+                    keep = active.nonzero(as_tuple=True)[0]
+                    idx = idx[keep]
+                    xw, mw, qw, fw = x[idx].contiguous(), meas[idx].contiguous(), qw[keep].contiguous(), fw[keep]
+                    prev, stall, active = prev[keep], stall[keep], active[keep]
             if max_total_iters is not None and total >= max_total_iters:
+                done = True
                 break
+        if xw is not x:
+            x[idx], qmu[idx], f_loss[idx] = xw, qw, fw
+        else:
+            qmu, f_loss = qw, fw
         t *= t_step
         if do_alpha_decay:
             alpha = alpha * math.sqrt(t_step)
             n_iter = min(int(n_iter / t_step), max_iter)
-        if max_total_iters is not None and total >= max_total_iters:
+        if done:
             break
-    return x, dict(iters=total, loss=f_loss, trace=trace)
+    return x, dict(iters=total, loss=f_loss, trace=trace, slice_iters=slice_iters)
 
 
 def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=1e-2, clip_concentrations=True,
