@@ -267,12 +267,16 @@ def run_gpu(args):
     h_out = torch.empty((S, K, N, N), dtype=torch.float32).pin_memory()
     h_loss = torch.empty((S,), dtype=torch.float64).pin_memory()
 
-    # Every step uploads ITS inputs and downloads ITS results; uploads of step i+1 and downloads of step i-1
-    # overlap the kernels of step i on separate streams (double-buffered device copies).
+    # Every step uploads ITS inputs and downloads ITS results.  The step's slices travel in sub-batches of SUB
+    # slices (one float4 group each at K = 2): the upload of sub-batch j+1 and the download of sub-batch j-1 overlap
+    # the kernels of sub-batch j on separate streams (double-buffered device copies), so only the first upload and
+    # the last download of the timed region are exposed.
+    SUB = 2 if S % 2 == 0 else S
+    nsub = S // SUB
     s_up, s_cmp, s_dn = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    xd = [torch.empty_like(x0) for _ in range(2)]
-    md = [torch.empty_like(meas) for _ in range(2)]
-    ld = [torch.empty((S,), dtype=torch.float64, device=dev) for _ in range(2)]
+    xd = [torch.empty_like(x0[:SUB]) for _ in range(2)]
+    md = [torch.empty_like(meas[:SUB]) for _ in range(2)]
+    ld = [torch.empty((SUB,), dtype=torch.float64, device=dev) for _ in range(2)]
     ev_up = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
@@ -280,24 +284,24 @@ def run_gpu(args):
     def e2e_steps(n_steps):
         for e in ev_free:
             e.record()
-        for i in range(n_steps):
-            b = i & 1
+        for i in range(n_steps * nsub):
+            b, j = i & 1, (i % nsub) * SUB
             with torch.cuda.stream(s_up):
                 s_up.wait_event(ev_free[b])
-                xd[b].copy_(h_x, non_blocking=True)
-                md[b].copy_(h_meas, non_blocking=True)
+                xd[b].copy_(h_x[j:j + SUB], non_blocking=True)
+                md[b].copy_(h_meas[j:j + SUB], non_blocking=True)
                 ev_up[b].record()
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_up[b])
                 _, qmu, l_ = proj.white_fp(spec, xd[b], meas=md[b], want_intensity=False)
-                g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+                g = proj.bp(qmu.reshape((SUB * K,) + proj.sino_shape), scale=-1.0)
                 p_ = proj.barrier_update(xd[b], g, alpha, beta, t_bar, reg_w=ir_beta, want_penalty=True)
                 torch.add(l_, p_, out=ld[b])
                 ev_done[b].record()
             with torch.cuda.stream(s_dn):
                 s_dn.wait_event(ev_done[b])
-                h_out.copy_(xd[b], non_blocking=True)
-                h_loss.copy_(ld[b], non_blocking=True)
+                h_out[j:j + SUB].copy_(xd[b], non_blocking=True)
+                h_loss[j:j + SUB].copy_(ld[b], non_blocking=True)
                 ev_free[b].record()
         cur = torch.cuda.current_stream()
         for st in (s_up, s_cmp, s_dn):
@@ -368,7 +372,8 @@ def run_gpu(args):
                 "ms_per_step": e2e_elapsed / args.steps * 1e3,
                 "what": "every step: pinned host concentrations + measured sinograms -> device, one barrier iteration "
                         "through Projector.white_fp/bp/barrier_update, updated concentrations + loss -> pinned host; "
-                        "copies of neighbouring steps overlap the kernels on separate streams"},
+                        "the slices of a step travel in sub-batches of 2 whose copies overlap the kernels of the "
+                        "neighbouring sub-batch on separate streams"},
         "gpu_launches": 7 * args.steps,   # per step: pack_vol, fp, reduce, pack_sino, bp, barrier_update, reduce
         "clocks": clocks,
         "loss_after": final_loss,
