@@ -332,3 +332,49 @@ def test_active_set_compaction_is_bit_identical_and_saves_work(golden):
     spent = int(ia["slice_iters"].sum().item())
     assert spent < ia["iters"] * S                      # some slices did stop early ...
     assert len(set(ia["slice_iters"].tolist())) > 1     # ... at different times
+
+
+def test_soft_inequality_least_squares_scipy_cg_over_the_drop_in():
+    """teeth_recon/experiments.py:513-582 (ineq_linear_least_squares): the reference's closures -- including its
+    literal `d[1-m]` integer indexing, which only ever touches d[0] and d[1] -- handed to scipy.optimize.fmin_cg
+    run unchanged over gpu_fp/gpu_bp and track the same closures over the oracle."""
+    import scipy.optimize as opt
+    from whitomo_b200 import astra_proxy as ap
+    n, na = 32, 40
+    pg = ap.astra.create_proj_geom('parallel', 1.0, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    vg = ap.astra.create_vol_geom(n, n)
+    pid = ap.astra.create_projector('linear', pg, vg)
+    g = oracle.Geometry.standard(n, na)
+    ph = np.zeros((n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    ph[(xx - 15.5) ** 2 + (yy - 15.5) ** 2 <= 144] = 0.10358164
+    ph[(xx - 18) ** 2 + (yy - 12) ** 2 <= 9] = 9.21754054
+    rng = np.random.RandomState(12345)
+    i0, bound, alpha = 1e9, 8.0, 300.0
+    pr = rng.poisson(lam=np.exp(np.log(i0) - oracle.fp(g, ph).astype(np.float64)).flatten()).astype('float32').reshape(g.sino_shape)
+    r, m = ob.ray_transform_from_projection(pr.copy(), bound, i0)
+    m = m.flatten()
+    b = r.flatten()
+    b[m] = np.log(i0) - np.log(bound)
+    n_bad = np.sum(m)
+    n_good = m.size - n_bad
+
+    def closures(FP, BP):
+        def weigh(x, good_w, bad_w):
+            d = FP(x) - b
+            d[(d > 0) * m] = 0.0
+            d[m] *= alpha
+            d[1 - m] /= good_w                 # the reference's literal indexing (elements 0 and 1 only)
+            d[m] /= bad_w
+            return d
+        return (lambda x: np.sum(weigh(x, np.sqrt(n_good), np.sqrt(n_bad)) ** 2)), (lambda x: 2.0 * BP(weigh(x, n_good, n_bad)))
+
+    dev_c = closures(lambda x: ap.gpu_fp(pg, vg, x.reshape(n, n), pid).flatten(),
+                     lambda x: ap.gpu_bp(pg, vg, x.reshape(g.sino_shape), pid).flatten())
+    cpu_c = closures(lambda x: oracle.fp(g, x.reshape(n, n)).flatten(),
+                     lambda x: oracle.bp(g, x.reshape(g.sino_shape)).flatten())
+    x0 = np.zeros(n * n, dtype='float32')
+    xd = opt.fmin_cg(dev_c[0], x0, dev_c[1], maxiter=6, disp=False)
+    xc = opt.fmin_cg(cpu_c[0], x0, cpu_c[1], maxiter=6, disp=False)
+    assert rel_l2(xd, xc) < 5e-3
+    assert dev_c[0](xd) < dev_c[0](x0.astype(np.float64))
