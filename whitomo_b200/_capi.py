@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwhitomo_b200.so")
+LIB_PATH = os.environ.get("WT_LIB", os.path.join(_HERE, "libwhitomo_b200.so"))   # WT_LIB: tuning builds only
 
 c_int, c_float, c_double, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p
 

@@ -25,9 +25,15 @@ constexpr int FP_DT = 32;       // detectors per CTA
 constexpr int FP_AT = 8;        // angles per CTA (one angle tile)
 constexpr int FP_THREADS = FP_DT * FP_AT;  // consumer threads (one ray each)
 constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only drives the TMA pipeline
-constexpr int FP_LB = 16;       // lines per staged chunk
+#ifndef WT_FP_LB
+#define WT_FP_LB 16
+#endif
+#ifndef WT_FP_STAGES
+#define WT_FP_STAGES 2
+#endif
+constexpr int FP_LB = WT_FP_LB;  // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
-constexpr int FP_STAGES = 4;
+constexpr int FP_STAGES = WT_FP_STAGES;
 constexpr int FP_SWEEP_TILES = 4;  // angle tiles per sweep direction (~ one wave of 148 x 2 resident CTAs; measured: 1,2,3,4,6,8 -> 1.80, 1.29, 0.98, 0.81, 1.08, 1.31 GB)
 // budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
 // for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
