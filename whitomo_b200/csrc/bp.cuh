@@ -140,17 +140,17 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 
     // this thread's pixels: columns lane, lane+32; rows warp, warp+8, warp+16, warp+24 (clamped into the
     // real tile so that every smem index stays inside the staged segment; clamped results are dropped)
-    float jc[2], ir[4];
+    float jc[2], ir[BP_RPT];
 #pragma unroll
     for (int c = 0; c < 2; ++c) jc[c] = (float)min(lane + 32 * c, tw - 1);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) ir[r] = (float)min(warp + 8 * r, th - 1);
+    for (int r = 0; r < BP_RPT; ++r) ir[r] = (float)min(warp + 8 * r, th - 1);
 
     constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
     constexpr int MAGIC_BITS = 0x4B400000;
-    float acc[4][2][V];
+    float acc[BP_RPT][2][V];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < BP_RPT; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
             const float2 c2 = sm.cst2[s][k];
             const VecT *seg = &sm.seg[s][k][0];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < BP_RPT; ++r) {
                 const float dr = fmaf(ir[r], c4.y, c4.z);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     }
 
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < BP_RPT; ++r) {
         const int row = row0 + warp + 8 * r;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
