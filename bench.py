@@ -43,9 +43,9 @@ def onchip_ceiling():
 
 def ncu_traffic(kernel, slices):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-    command at the same slices-per-step (profiles/r1_traffic_s8.json); None for any other configuration."""
+    command at the same slices-per-step (profiles/r1_traffic_s8_v2.json); None for any other configuration."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic_s8.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic_s8_v2.json")) as f:
             t = json.load(f)
         return float(t[kernel]["traffic_bytes"]) if slices == 8 else None
     except Exception:
@@ -381,9 +381,10 @@ def run_gpu(args):
             "not HBM (SURVEY 8d: compulsory-bytes ceiling of the HBM fraction is ~0.4%)")
     r_fp = dict(roof(fp_bytes, t_fp, "fp"), kernel="fp_kernel<4, white epilogue> (TMA-staged ray-driven Joseph FP), "
                 "%.0f%% of the step" % (100 * t_fp / tot),
-                note=note + "; DRAM traffic stays a few times the algorithmic bytes because a float4 group's packed "
-                "volume copy (67 MB) exceeds the effective L2 share and every wave of CTAs sweeps it (alternating the "
-                "sweep direction per wave cut it 2.5x) -- ~2% of DRAM bandwidth, off the critical path")
+                note=note + "; DRAM traffic is 1.5x the algorithmic bytes: the projector reads two packed copies of "
+                "the volume (row-major for vertical angles, transposed for horizontal ones) where the algorithmic "
+                "count has one; the detector-block-major launch order keeps the lines in flight L2-resident, so each "
+                "copy comes from DRAM once (tile-major order read 9.2 GB, with alternating sweeps 4.1 GB)")
     r_bp = dict(roof(bp_bytes, t_bp, "bp"), kernel="bp_kernel<4> (TMA-staged pixel-driven gather), %.0f%% of the step"
                 % (100 * t_bp / tot), note=note)
     out["roofline"], out["roofline_other"] = (r_fp, r_bp) if t_fp >= t_bp else (r_bp, r_fp)    # dominant kernel first

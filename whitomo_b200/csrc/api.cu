@@ -60,12 +60,6 @@ static std::vector<Chunk> chunks(int n, int multiple_of = 1) {
     return c;
 }
 
-static int sweep_tiles() {
-    static int v = 0;
-    if (!v) { const char *e = getenv("WT_FP_SWEEP_TILES"); v = e ? atoi(e) : FP_SWEEP_TILES; if (v < 1) v = 1; }
-    return v;
-}
-
 // Images are processed in chunks of V in {4,2,1} interleaved images.  Calls with one or two images in total use
 // mirror pairing instead (each image also travels as its point reflection: V = 2n components, half the rays).
 // Pairing halves the number of CTAs, so it only pays once the backprojector still fills the GPU with half its pixel
@@ -82,7 +76,10 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     p.vn = vn; p.vt = vt; p.ang = g->d_fp;
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
     p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
-    p.a_begin = a_begin; p.a_end = a_end; p.sweep_tiles = sweep_tiles();
+    p.a_begin = a_begin; p.a_end = a_end;
+    p.order = g->d_order; p.nphase = g->nphase;
+    for (int i = 0; i <= FP_MAX_PHASES; ++i) p.phase_start[i] = g->phase_start[i];
+    p.ndblk = 0;   // set by launch_fp from Dproc
     if (use_mirror(g, n)) {
         p.Dproc = (g->ndet + 1) / 2;
         Epi epi = epi_proto.offset(0);
@@ -285,6 +282,25 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
             a += cnt;
         }
     }
+    // launch order: one phase per orientation (fp.cuh: fp_block); WT_FP_PHASES = 1 | 2 | 4 for experiments
+    // (1: all tiles in one phase, 4: orientation x slope sign)
+    std::vector<int> order;
+    int phase_start[FP_MAX_PHASES + 1] = {0, 0, 0, 0, 0}, nphase = 0;
+    {
+        const char *e = getenv("WT_FP_PHASES");
+        int want = e ? atoi(e) : 2;
+        if (want != 1 && want != 4) want = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            for (int t = 0; t < (int)tiles.size(); ++t) {
+                const FpAngle &f = fp[tiles[t].first + tiles[t].count / 2];
+                const int key = (f.vertical ? 0 : 2) + (f.delta < 0.0f ? 1 : 0);
+                const int mine = want == 4 ? key : want == 2 ? (key & 2) : 0;
+                if (mine == ph) order.push_back(t);
+            }
+            if ((int)order.size() > phase_start[nphase]) { ++nphase; phase_start[nphase] = (int)order.size(); }
+        }
+        for (int i = nphase + 1; i <= FP_MAX_PHASES; ++i) phase_start[i] = phase_start[nphase];
+    }
     wt_geom *g = new wt_geom();
     g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
     // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row
@@ -294,7 +310,9 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
     g->sino_pitch = (padl + ndet + padl + BP_SEGW + 3) & ~3;
-    g->d_fp = nullptr; g->d_bp = nullptr; g->d_tiles = nullptr;
+    g->d_fp = nullptr; g->d_bp = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
+    g->nphase = nphase;
+    for (int i = 0; i <= FP_MAX_PHASES; ++i) g->phase_start[i] = phase_start[i];
     g->ntiles = (int)tiles.size();
     g->h_angles = (float *)malloc(sizeof(float) * nangles);
     memcpy(g->h_angles, angles, sizeof(float) * nangles);
@@ -304,6 +322,8 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     if (e == cudaSuccess) e = cudaMemcpy(g->d_bp, bp.data(), sizeof(BpAngle) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_tiles, sizeof(FpTile) * tiles.size());
     if (e == cudaSuccess) e = cudaMemcpy(g->d_tiles, tiles.data(), sizeof(FpTile) * tiles.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_order, sizeof(int) * order.size());
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         wt_geom_destroy(g);
         return cuda_fail(e, "wt_geom_create");
@@ -317,6 +337,7 @@ void wt_geom_destroy(wt_geom *g) {
     if (g->d_fp) cudaFree(g->d_fp);
     if (g->d_bp) cudaFree(g->d_bp);
     if (g->d_tiles) cudaFree(g->d_tiles);
+    if (g->d_order) cudaFree(g->d_order);
     free(g->h_angles);
     delete g;
 }

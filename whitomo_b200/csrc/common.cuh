@@ -70,6 +70,9 @@ struct wt_geom {
     wt::BpAngle *d_bp;
     void *d_tiles;   // wt::FpTile[ntiles]: angle tiles of the forward projector
     int ntiles;
+    int *d_order;    // launch order of the tiles, phase by phase (fp.cuh: fp_block)
+    int nphase;
+    int phase_start[5];
     float *h_angles;
 };
 

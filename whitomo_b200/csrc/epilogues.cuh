@@ -63,8 +63,8 @@ struct FpEpiWhite {
         constexpr int SPG = V / K;
         __shared__ float red[SPG][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
-        const int nblocks = gridDim.x * gridDim.y * npass;
-        const int bid = pass * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
+        const int nblocks = p.ndblk * p.ntiles * npass;
+        const int bid = pass * p.ndblk * p.ntiles + fp_block_id(p);
         const int tid = threadIdx.x;
         // spectrum tables -> shared memory (the projector's staging buffers are idle now): broadcast LDS in the bin loop
         const int ntab = (K + 1) * E;
@@ -131,8 +131,8 @@ struct FpEpiMar {
                                                const float (&val)[V], float *, int pass, int npass) const {
         __shared__ float red[3][V][FP_BLOCK / 32];
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
-        const int nblocks = gridDim.x * gridDim.y * npass;
-        const int bid = pass * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x;
+        const int nblocks = p.ndblk * p.ntiles * npass;
+        const int bid = pass * p.ndblk * p.ntiles + fp_block_id(p);
         const int tid = threadIdx.x;
         if (partial) __syncthreads();   // a previous pass may still be reading `red`
 #pragma unroll

@@ -34,10 +34,10 @@ constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only driv
 constexpr int FP_LB = WT_FP_LB;  // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
 constexpr int FP_STAGES = WT_FP_STAGES;
-constexpr int FP_SWEEP_TILES = 4;  // angle tiles per sweep direction (~ one wave of 148 x 2 resident CTAs; measured: 1,2,3,4,6,8 -> 1.80, 1.29, 0.98, 0.81, 1.08, 1.31 GB)
 // budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
 // for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
 constexpr int FP_WFIT = FP_W - 8;
+constexpr int FP_MAX_PHASES = 4;
 
 __host__ __device__ inline int fp_pitch(int npos) {
     int p = npos + 2 * VPAD;
@@ -114,8 +114,40 @@ struct FpParams {
     int R, C, D, A;
     int Dproc;         // detectors that get a thread: D, or ceil(D/2) under mirror pairing
     int a_begin, a_end;
-    int sweep_tiles;   // angle tiles per sweep direction (FP_SWEEP_TILES)
+    // CTA launch order (see fp_block): tiles grouped into phases (one per orientation)
+    const int *order;  // tile indices, phase by phase
+    int nphase;
+    int phase_start[FP_MAX_PHASES + 1];  // prefix offsets into `order`
+    int ndblk;         // detector blocks per tile
 };
+
+// Launch order.  The grid is linear in x: phase by phase (vertical angles read VN, horizontal angles VT), inside a
+// phase detector block by detector block, inside a detector block all the phase's angle tiles.  The rays of one
+// detector block over all angles of a phase cover a "bow tie" of the packed volume copy (at most ~60 % of it, 40 MB
+// of a float4 group's 67 MB at 2048^2) that slides by FP_DT positions per detector block, so the lines the resident CTAs read stay in L2 until the
+// fan has moved past them and every line comes from DRAM about once per phase.  Measured (ncu, one float4 group at
+// 2048^2 x 1800): 156 MB read for 134 MB of packed copies with one phase per orientation; tile-major order -- every
+// wave of CTAs sweeping a whole copy that exceeds the ~60 MB effective L2 share -- read 2.3 GB, 0.81 GB with the sweep
+// direction alternating per wave; four phases (orientation x slope sign) read each copy twice, 200 MB.
+// Logical indices, not blockIdx, name a CTA's partial-sum slot, so results do not depend on the launch order.
+struct FpBlock { int tile, dblk; };
+__device__ __forceinline__ FpBlock fp_block(const FpParams &p) {
+    // static indices only: a dynamically indexed kernel-parameter array would be copied to local memory
+    const int lin0 = blockIdx.x;
+    int s0 = 0, s1 = p.phase_start[1];
+#pragma unroll
+    for (int ph = 1; ph < FP_MAX_PHASES; ++ph)
+        if (ph < p.nphase && lin0 >= p.phase_start[ph] * p.ndblk) { s0 = p.phase_start[ph]; s1 = p.phase_start[ph + 1]; }
+    const int lin = lin0 - s0 * p.ndblk, nt = s1 - s0;
+    FpBlock b;
+    b.dblk = lin / nt;
+    b.tile = __ldg(p.order + s0 + (lin - b.dblk * nt));
+    return b;
+}
+__device__ __forceinline__ int fp_block_id(const FpParams &p) {   // tile-major id, as (blockIdx.y, blockIdx.x) used to be
+    const FpBlock b = fp_block(p);
+    return b.tile * p.ndblk + b.dblk;
+}
 
 // plain store: sino (n, A, D)
 struct FpEpiStore {
@@ -154,9 +186,10 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp = 16 detectors x 2 angles; quarter-warp = 4 detectors x 2 angles
     const int slot = (warp >> 1) * 2 + (lane & 1);
-    const int d0 = blockIdx.x * FP_DT;
+    const FpBlock blk = fp_block(p);
+    const int d0 = blk.dblk * FP_DT;
     const int d = d0 + (warp & 1) * 16 + (lane >> 3) * 4 + ((lane >> 1) & 3);
-    const FpTile tile = p.tiles[blockIdx.y];
+    const FpTile tile = p.tiles[blk.tile];
     const int a = tile.first + slot;
     const int g = blockIdx.z;
     const bool producer = warp == FP_THREADS / 32;
@@ -232,16 +265,10 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const bool tile_in_range = tile.first < p.a_end && tile.first + tile.count > p.a_begin;   // CTA-uniform
     const int nchunk = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
 
-    // Sweep direction alternates every FP_SWEEP_TILES angle tiles (about one wave of resident CTAs): a float4 group's
-    // packed copy (67 MB at 2048^2) does not fit the effective L2 share, and same-direction sweeps of consecutive
-    // waves evict every line before its re-use (ncu: 16x the compulsory DRAM reads).  Sweeping back over the lines
-    // the previous wave touched last turns most of those misses into L2 hits.  A ray's sum order depends only on
-    // its tile index, so results stay deterministic and independent of batch composition and angle range.
-    const bool reverse = ((blockIdx.y / p.sweep_tiles) & 1) != 0;
-    // producer warp: stage chunk `ch` = the ch-th chunk of FP_LB lines in sweep order
+    // producer warp: stage chunk `ch` = the ch-th chunk of FP_LB lines (ascending, the reference's summation order)
     auto produce = [&](int ch) {
         const int s = ch % FP_STAGES;
-        const int l0 = Lb + (reverse ? nchunk - 1 - ch : ch) * FP_LB;
+        const int l0 = Lb + ch * FP_LB;
         const int l1 = min(l0 + FP_LB, nlines) - 1;
         // left-most position any ray of the tile takes on these lines (linear in l: attained at an end)
         float m = 3.0e38f;
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         for (int ch = 0; ch < nchunk; ++ch) {
             const int s = ch % FP_STAGES;
             mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
-            const int l0 = Lb + (reverse ? nchunk - 1 - ch : ch) * FP_LB;
+            const int l0 = Lb + ch * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
             if (la < lb) {
                 // c - 0.5 relative to the window start at line la; then one FADD per line
@@ -340,8 +367,10 @@ inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cuda
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.Dproc + FP_DT - 1) / FP_DT, p.ntiles, groups);
-    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(p, epi);
+    FpParams q = p;
+    q.ndblk = (p.Dproc + FP_DT - 1) / FP_DT;
+    dim3 grid(q.ndblk * p.ntiles, 1, groups);
+    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(q, epi);
     return cudaSuccess;
 }
 
