@@ -124,8 +124,8 @@ struct FpParams {
 // Launch order.  The grid is linear in x: phase by phase (vertical angles read VN, horizontal angles VT), inside a
 // phase detector block by detector block, inside a detector block all the phase's angle tiles.  The rays of one
 // detector block over all angles of a phase cover a "bow tie" of the packed volume copy (at most ~60 % of it, 40 MB
-// of a float4 group's 67 MB at 2048^2) that slides by FP_DT positions per detector block, so the lines the resident CTAs read stay in L2 until the
-// fan has moved past them and every line comes from DRAM about once per phase.  Measured (ncu, one float4 group at
+// of a float4 group's 67 MB at 2048^2) that slides by FP_DT positions per detector block, so the lines the resident
+// CTAs read stay in L2 until the bow tie has moved past them and every line comes from DRAM about once per phase.  Measured (ncu, one float4 group at
 // 2048^2 x 1800): 156 MB read for 134 MB of packed copies with one phase per orientation; tile-major order -- every
 // wave of CTAs sweeping a whole copy that exceeds the ~60 MB effective L2 share -- read 2.3 GB, 0.81 GB with the sweep
 // direction alternating per wave; four phases (orientation x slope sign) read each copy twice, 200 MB.
@@ -134,6 +134,12 @@ struct FpBlock { int tile, dblk; };
 __device__ __forceinline__ FpBlock fp_block(const FpParams &p) {
     // static indices only: a dynamically indexed kernel-parameter array would be copied to local memory
     const int lin0 = blockIdx.x;
+    if (p.nphase == 0) {   // tile-major, detector blocks fastest (WT_FP_ORDER=tile, kept for A/B measurements)
+        FpBlock b;
+        b.tile = lin0 / p.ndblk;
+        b.dblk = lin0 - b.tile * p.ndblk;
+        return b;
+    }
     int s0 = 0, s1 = p.phase_start[1];
 #pragma unroll
     for (int ph = 1; ph < FP_MAX_PHASES; ++ph)
