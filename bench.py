@@ -355,13 +355,15 @@ def run_gpu(args):
         "barrier_iters_per_s": S * world * args.steps / elapsed,
         "fp_gups": K * N * N * A * S / t_fp / 1e9, "bp_gups": K * N * N * A * S / t_bp / 1e9,
         "kernel_ms": {"white_fp": t_fp * 1e3, "bp": t_bp * 1e3, "barrier_update": t_up * 1e3},
-        # K2 performs exactly N^2*A tap pairs per image; K1 only N^2*A*mean(max(|cos|,|sin|)) of them (rays are spaced
-        # 1/max(|cos|,|sin|) positions apart on a line), so in the metric's nominal updates K1's ceiling is higher
-        "onchip": {"bound": "shared-memory load bandwidth (2 taps x 16 B per 4 updates)", "peak_gups": ceil_gups,
+        # shared-memory bytes per update: K1 reads 2 taps x 16 B per 4 updates, but only N^2*A*mean(max(|cos|,|sin|)) tap
+        # pairs per image (rays are 1/max(|cos|,|sin|) positions apart on a line); K2 reads 3 taps x 16 B per 8 updates
+        # (a vertically adjacent pixel pair shares its taps), i.e. 6 B per update where separate taps would need 8
+        "onchip": {"bound": "shared-memory load bandwidth (LDS.128 wavefronts)", "peak_gups_at_8B_per_update": ceil_gups,
                    "peak_source": ceil_src, "fp_work_factor": fp_work,
-                   "fp_peak_gups_nominal": ceil_gups / fp_work,
+                   "fp_bytes_per_update": 8.0 * fp_work, "bp_bytes_per_update": 6.0,
+                   "fp_peak_gups": ceil_gups / fp_work, "bp_peak_gups": ceil_gups * 8.0 / 6.0,
                    "fp_frac": K * N * N * A * S / t_fp / 1e9 / (ceil_gups / fp_work),
-                   "bp_frac": K * N * N * A * S / t_bp / 1e9 / ceil_gups},
+                   "bp_frac": K * N * N * A * S / t_bp / 1e9 / (ceil_gups * 8.0 / 6.0)},
         "roofline": None, "roofline_other": None,
         "roofline_update": dict(roof(up_bytes, t_up, "update"), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3)"),
         "e2e": {"value": upd_per_step * args.steps / e2e_elapsed / 1e9, "unit": UNIT,

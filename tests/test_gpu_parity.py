@@ -285,3 +285,47 @@ def test_empty_batch_and_zero_iterations(eng):
     z = P.sirt(torch.rand(6, 23, device="cuda"), 0)
     assert z.shape == (16, 16) and torch.count_nonzero(z).item() == 0
     assert torch.count_nonzero(P.fp(torch.zeros(16, 16, device="cuda"))).item() == 0
+
+
+def test_one_projector_on_two_streams(eng):
+    """calls issued on different CUDA streams may overlap on the device: each stream gets its own scratch, so the
+    results equal those of the same calls issued one after the other"""
+    Projector, _ = eng
+    n, a = 192, 120
+    d = int(np.sqrt(2) * n + 1)
+    P = Projector(n, n, d, np.linspace(0, np.pi, a))
+    x1 = torch.from_numpy(np.stack([phantom(n, seed=s) for s in range(4)])).cuda()
+    x2 = torch.from_numpy(np.stack([phantom(n, seed=10 + s) for s in range(4)])).cuda()
+    ref = [P.fp(x1).clone(), P.fp(x2).clone(), P.bp(P.fp(x1)).clone(), P.bp(P.fp(x2)).clone()]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            p1 = P.fp(x1)
+            v1 = P.bp(p1)
+        with torch.cuda.stream(s2):
+            p2 = P.fp(x2)
+            v2 = P.bp(p2)
+        torch.cuda.synchronize()
+        for got, want in zip((p1, p2, v1, v2), ref):
+            assert torch.equal(got, want)
+    assert len(P._ws) >= 2
+
+
+@pytest.mark.parametrize("det_width", [1.0, 1.25, 2.0])
+def test_wide_detector_pixels_and_unordered_angles(eng, det_width):
+    """detector pixels wider than a volume pixel (create_proj_geom's det_width argument) and an angle list that is
+    unsorted, repeats a view and leaves [0, pi)"""
+    Projector, _ = eng
+    r, c, d = 70, 90, 101
+    ang = np.array([2.1, -0.4, 0.0, 3.9, 0.77, 0.77, 1.5707963, 6.0, 1.2, 2.8, -2.2])
+    g = oracle.Geometry(r, c, d, ang, det_width=det_width)
+    P = Projector(r, c, d, ang, det_width=det_width)
+    x = np.stack([phantom(r, c, s) for s in range(5)])
+    y = np.random.default_rng(8).random((5,) + g.sino_shape).astype(np.float32)
+    p = P.fp(torch.from_numpy(x).cuda()).cpu().numpy()
+    v = P.bp(torch.from_numpy(y).cuda()).cpu().numpy()
+    for i in range(5):
+        assert rel_l2(p[i], oracle.fp(g, x[i])) < TOL_OP
+        assert rel_l2(v[i], oracle.bp(g, y[i])) < TOL_OP
+    assert np.array_equal(p[:, 4], p[:, 5])                # the repeated view

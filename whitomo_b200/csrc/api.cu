@@ -47,31 +47,26 @@ static size_t packed_vol_floats(const wt_geom *g, int n) {
 static size_t packed_sino_floats(const wt_geom *g, int n) { return align_up((size_t)n * g->nangles * g->sino_pitch, 64); }
 static int fp_blocks(const wt_geom *g) { return ((g->ndet + FP_DT - 1) / FP_DT) * g->ntiles; }
 
-// images are processed in chunks of V in {4,2,1} interleaved images
-struct Chunk { int v, first, groups; };
-static std::vector<Chunk> chunks(int n, int multiple_of = 1) {
-    std::vector<Chunk> c;
-    int first = 0;
-    for (int v = 4; v >= 1; v >>= 1) {
-        if (v % multiple_of) continue;
-        const int gcount = (n - first) / v;
-        if (gcount > 0) { c.push_back({v, first, gcount}); first += gcount * v; }
-    }
-    return c;
+// Images are processed in groups of V interleaved images.  Three or more images always go through the float4
+// kernels, the last group padded with zero components (never stored) when the count is not a multiple of four: an
+// image's bits then do not depend on how many images travel with it, and a padded float4 group is cheaper than the
+// float2 + float kernels it replaces.  One or two images run as a float2 / float group, or mirror-paired (below).
+struct Chunk { int v, groups; };
+static Chunk chunk_of(int n) {
+    if (n >= 3) return {4, (n + 3) / 4};
+    return {n, 1};
 }
 
-// Images are processed in chunks of V in {4,2,1} interleaved images.  Calls with one or two images in total use
-// mirror pairing instead (each image also travels as its point reflection: V = 2n components, half the rays).
+// Calls with one or two images of a large volume use mirror pairing instead (each image also travels as its point reflection: V = 2n components, half the rays).
 // Pairing halves the number of CTAs, so it only pays once the backprojector still fills the GPU with half its pixel
 // tiles: images of at least 768^2 pixels (measured: 1.3-1.7x faster at 1024^2 and up, slower at 512^2 and below).
 static inline bool use_mirror(const wt_geom *g, int n) { return n <= 2 && (size_t)g->rows * g->cols >= (size_t)768 * 768; }
-static inline int packed_images(const wt_geom *g, int n) { return use_mirror(g, n) ? 2 * n : n; }
+static inline int packed_images(const wt_geom *g, int n) { return use_mirror(g, n) ? 2 * n : chunk_of(n).v * chunk_of(n).groups; }
 
 // returns the number of per-image partial-sum slots the epilogue wrote (CTAs x passes), or a negative error
 template <class Epi>
 static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_end, float *vn, float *vt,
-                  const Epi &epi_proto, cudaStream_t st, int multiple_of = 1) {
-    const size_t img = (size_t)g->rows * g->cols;
+                  const Epi &epi_proto, cudaStream_t st) {
     FpParams p;
     p.vn = vn; p.vt = vt; p.ang = g->d_fp;
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
@@ -81,121 +76,75 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     { const char *e = getenv("WT_FP_ORDER"); if (e && !strcmp(e, "tile")) p.nphase = 0; }
     for (int i = 0; i <= FP_MAX_PHASES; ++i) p.phase_start[i] = g->phase_start[i];
     p.ndblk = 0;   // set by launch_fp from Dproc
+    p.nimg = n;
+    const Epi epi = epi_proto;
     if (use_mirror(g, n)) {
         p.Dproc = (g->ndet + 1) / 2;
-        Epi epi = epi_proto.offset(0);
         if (n == 1) {
             if constexpr (Epi::kMult == 1) {
-                launch_pack_vol<2, true>(vol, vn, vt, p.R, p.C, 1, st);
+                launch_pack_vol<2, true>(vol, vn, vt, p.R, p.C, 1, n, st);
                 WT_CUDA((launch_fp<2, Epi, true>(p, epi, 1, st)));
             } else {
                 return invalid("run_fp: image count is not a multiple of the element count");
             }
         } else {
-            launch_pack_vol<4, true>(vol, vn, vt, p.R, p.C, 1, st);
+            launch_pack_vol<4, true>(vol, vn, vt, p.R, p.C, 1, n, st);
             WT_CUDA((launch_fp<4, Epi, true>(p, epi, 1, st)));
         }
         WT_CUDA(cudaGetLastError());
         return 2 * ((p.Dproc + FP_DT - 1) / FP_DT) * g->ntiles;
     }
     p.Dproc = g->ndet;
-    for (const Chunk &c : chunks(n, multiple_of)) {
-        const float *src = vol + (size_t)c.first * img;
-        Epi epi = epi_proto.offset(c.first);
-        switch (c.v) {
-        case 4: launch_pack_vol<4>(src, vn, vt, p.R, p.C, c.groups, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
-        case 2:
-            if constexpr (2 % Epi::kMult == 0) { launch_pack_vol<2>(src, vn, vt, p.R, p.C, c.groups, st); WT_CUDA((launch_fp<2, Epi>(p, epi, c.groups, st))); }
-            break;
-        default:
-            if constexpr (Epi::kMult == 1) { launch_pack_vol<1>(src, vn, vt, p.R, p.C, c.groups, st); WT_CUDA((launch_fp<1, Epi>(p, epi, c.groups, st))); }
-            break;
-        }
-        WT_CUDA(cudaGetLastError());
+    if (n % Epi::kMult) return invalid("run_fp: image count is not a multiple of the element count");
+    const Chunk c = chunk_of(n);
+    switch (c.v) {
+    case 4: launch_pack_vol<4>(vol, vn, vt, p.R, p.C, c.groups, n, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
+    case 2:
+        if constexpr (2 % Epi::kMult == 0) { launch_pack_vol<2>(vol, vn, vt, p.R, p.C, 1, n, st); WT_CUDA((launch_fp<2, Epi>(p, epi, 1, st))); }
+        break;
+    default:
+        if constexpr (Epi::kMult == 1) { launch_pack_vol<1>(vol, vn, vt, p.R, p.C, 1, n, st); WT_CUDA((launch_fp<1, Epi>(p, epi, 1, st))); }
+        break;
     }
+    WT_CUDA(cudaGetLastError());
     return fp_blocks(g);
 }
 
 template <class Epi>
 static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
                   cudaStream_t st) {
-    const size_t plane = (size_t)g->nangles * g->ndet;
     BpParams p;
     p.sp = sp; p.ang = g->d_bp;
     p.R = g->rows; p.C = g->cols; p.A = g->nangles;
     p.padl = g->sino_padl; p.pitch = g->sino_pitch;
     p.a_begin = a_begin; p.a_end = a_end;
+    p.nimg = n;
+    const Epi epi = epi_proto;
     if (use_mirror(g, n)) {
         p.Rproc = (g->rows + 1) / 2;
-        Epi epi = epi_proto.offset(0);
-        if (n == 1) { launch_pack_sino<2, true>(sino, sp, g, 1, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
-        else { launch_pack_sino<4, true>(sino, sp, g, 1, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
+        if (n == 1) { launch_pack_sino<2, true>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
+        else { launch_pack_sino<4, true>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
         WT_CUDA(cudaGetLastError());
         return WT_OK;
     }
     p.Rproc = g->rows;
-    for (const Chunk &c : chunks(n)) {
-        const float *src = sino + (size_t)c.first * plane;
-        Epi epi = epi_proto.offset(c.first);
-        switch (c.v) {
-        case 4: launch_pack_sino<4>(src, sp, g, c.groups, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
-        case 2: launch_pack_sino<2>(src, sp, g, c.groups, st); WT_CUDA((launch_bp<2, Epi>(p, epi, c.groups, st))); break;
-        default: launch_pack_sino<1>(src, sp, g, c.groups, st); WT_CUDA((launch_bp<1, Epi>(p, epi, c.groups, st))); break;
-        }
-        WT_CUDA(cudaGetLastError());
+    const Chunk c = chunk_of(n);
+    switch (c.v) {
+    case 4: launch_pack_sino<4>(sino, sp, g, c.groups, n, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
+    case 2: launch_pack_sino<2>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
+    default: launch_pack_sino<1>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
     }
+    WT_CUDA(cudaGetLastError());
     return WT_OK;
 }
 
-// host-side wrappers that know how to shift their pointers to the first image of a chunk
-struct HFpStore : FpEpiStore {
-    static constexpr int kMult = 1;
-    size_t plane;
-    HFpStore offset(int first) const { HFpStore e = *this; e.sino = sino + (size_t)first * plane; return e; }
-};
-struct HFpSirt : FpEpiSirtResidual {
-    static constexpr int kMult = 1;
-    size_t plane;
-    HFpSirt offset(int first) const {
-        HFpSirt e = *this; e.meas = meas + (size_t)first * plane; e.out = out + (size_t)first * plane; return e;
-    }
-};
-struct HBpStore : BpEpiStore {
-    size_t img;
-    HBpStore offset(int first) const { HBpStore e = *this; e.vol = vol + (size_t)first * img; return e; }
-};
-struct HBpSirt : BpEpiSirtUpdate {
-    size_t img;
-    HBpSirt offset(int first) const { HBpSirt e = *this; e.vol = vol + (size_t)first * img; return e; }
-};
-struct HFpMar : FpEpiMar {
-    static constexpr int kMult = 1;
-    size_t plane;
-    int nblocks;
-    HFpMar offset(int first) const {
-        HFpMar e = *this;
-        e.b = b + (size_t)first * plane; e.mask = mask + (size_t)first * plane; e.inv_ngood = inv_ngood + first;
-        if (e.u) e.u += (size_t)first * plane;
-        if (e.proj) e.proj += (size_t)first * plane;
-        if (e.partial) e.partial += (size_t)first * nblocks;
-        return e;
-    }
-};
-template <int K>
-struct HFpWhite : FpEpiWhite<K> {
-    static constexpr int kMult = K;
-    size_t plane;
-    int nblocks;
-    HFpWhite offset(int first) const {
-        HFpWhite e = *this;
-        const size_t s0 = (size_t)first / K;
-        if (e.meas) e.meas += s0 * plane;
-        if (e.inten) e.inten += s0 * plane;
-        if (e.qmu) e.qmu += (size_t)first * plane;
-        if (e.partial) e.partial += s0 * nblocks;
-        return e;
-    }
-};
+// epilogues as the host instantiates them: kMult = images per problem (a group must hold whole problems)
+struct HFpStore : FpEpiStore { static constexpr int kMult = 1; };
+struct HFpSirt : FpEpiSirtResidual { static constexpr int kMult = 1; };
+struct HFpMar : FpEpiMar { static constexpr int kMult = 1; };
+template <int K> struct HFpWhite : FpEpiWhite<K> { static constexpr int kMult = K; };
+typedef BpEpiStore HBpStore;
+typedef BpEpiSirtUpdate HBpSirt;
 
 }  // namespace wt
 
@@ -373,7 +322,6 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angl
     float *vt = cv.take<float>(vt_floats(g, npack));
     HFpStore epi;
     epi.sino = sino;
-    epi.plane = (size_t)g->nangles * g->ndet;
     const int rc = run_fp(g, vol, nimages, angle_begin, angle_end, vn, vt, epi, (cudaStream_t)stream);
     return rc < 0 ? rc : WT_OK;
 }
@@ -394,7 +342,6 @@ int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned
     HFpMar e;
     e.b = b; e.mask = mask; e.inv_ngood = inv_ngood; e.bt = bt; e.b_hb = b_hb; e.u = u; e.proj = proj;
     e.partial = stats ? partial : nullptr; e.nimg = nimages;
-    e.plane = (size_t)g->nangles * g->ndet; e.nblocks = fp_blocks(g);
     const int nb = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, e, st);   // partial-sum slots per image
     if (nb < 0) return nb;
     if (stats) {
@@ -419,7 +366,6 @@ int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angl
     HBpStore epi;
     epi.vol = vol;
     epi.scale = scale;
-    epi.img = (size_t)g->rows * g->cols;
     return run_bp(g, sino, nimages, angle_begin, angle_end, sp, epi, (cudaStream_t)stream);
 }
 
@@ -446,19 +392,19 @@ int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_
     float *resid = cv.take<float>((size_t)nimages * plane);
     // Rsum = W 1, Csum = W^T 1 (the residual buffer doubles as the all-ones input)
     fill_kernel<<<296, 256, 0, st>>>(vol, img, 1.0f);
-    HFpStore fs; fs.sino = raysum; fs.plane = plane;
+    HFpStore fs; fs.sino = raysum;
     int rc = run_fp(g, vol, 1, 0, g->nangles, vn, vt, fs, st);
     if (rc < 0) return rc;
     fill_kernel<<<296, 256, 0, st>>>(resid, plane, 1.0f);
-    HBpStore bs; bs.vol = pixsum; bs.scale = 1.0f; bs.img = img;
+    HBpStore bs; bs.vol = pixsum; bs.scale = 1.0f;
     rc = run_bp(g, resid, 1, 0, g->nangles, sp, bs, st);
     if (rc) return rc;
     WT_CUDA(cudaMemsetAsync(vol, 0, sizeof(float) * nimages * img, st));
     for (int it = 0; it < n_iters; ++it) {
-        HFpSirt fe; fe.meas = sino; fe.raysum = raysum; fe.out = resid; fe.plane = plane;
+        HFpSirt fe; fe.meas = sino; fe.raysum = raysum; fe.out = resid;
         rc = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, fe, st);
         if (rc < 0) return rc;
-        HBpSirt be; be.vol = vol; be.pixsum = pixsum; be.img = img;
+        HBpSirt be; be.vol = vol; be.pixsum = pixsum;
         rc = run_bp(g, resid, nimages, 0, g->nangles, sp, be, st);
         if (rc) return rc;
     }
@@ -510,17 +456,17 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
         int rc;
         if (K == 1) {
             HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
-            e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
-            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st, 1);
+            e.partial = loss ? partial : nullptr;
+            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         } else {
             HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
-            e.partial = loss ? partial : nullptr; e.plane = plane; e.nblocks = nb;
-            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st, 2);
+            e.partial = loss ? partial : nullptr;
+            rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         }
         if (rc < 0) return rc;
         nb = rc;   // partial-sum slots per slice (CTAs x passes)
     } else {
-        HFpStore fs; fs.sino = sp; fs.plane = plane;
+        HFpStore fs; fs.sino = sp;
         int rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, fs, st);
         if (rc < 0) return rc;
         nb = (int)((plane + 255) / 256);

@@ -11,6 +11,8 @@
 // Lanes run along image columns: their detector positions differ by |cos| <= 1, so the LDS of a warp
 // touches at most 32 consecutive words -- conflict-free.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace wt {
@@ -20,7 +22,7 @@ namespace wt {
 // (pixel (R-1-row, C-1-col) sees detector coordinate (D-1) - d*, see the kernel's epilogue)
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict__ sino, float *__restrict__ sp, int A,
-                                                        int D, int padl, int pitch) {
+                                                        int D, int padl, int pitch, int nimg) {
     static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
     constexpr int V0 = MIRROR ? V / 2 : V;
@@ -32,23 +34,24 @@ __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict_
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const bool rev = MIRROR && i >= V0;
-            const size_t im = (size_t)g * V0 + (rev ? i - V0 : i);
-            v[i] = (d >= 0 && d < D) ? __ldg(sino + im * plane + (size_t)a * D + (rev ? D - 1 - d : d)) : 0.0f;
+            const size_t im = (size_t)g * V0 + (rev ? i - V0 : i);       // >= nimg: padding component of the last group
+            v[i] = (d >= 0 && d < D && im < (size_t)nimg) ? __ldg(sino + im * plane + (size_t)a * D + (rev ? D - 1 - d : d)) : 0.0f;
         }
         reinterpret_cast<VecT *>(sp)[((size_t)g * A + a) * pitch + dp] = pack<V>(v);
     }
 }
 
 template <int V, bool MIRROR = false>
-inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, cudaStream_t st) {
+inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, int nimg, cudaStream_t st) {
     dim3 grid((g->sino_pitch + 255) / 256, g->nangles, groups);
-    pack_sino_kernel<V, MIRROR><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch);
+    pack_sino_kernel<V, MIRROR><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch, nimg);
 }
 
 struct BpParams {
     const float *sp;  // packed sinogram (G, A, pitch, V)
     const BpAngle *ang;
     int R, C, A;
+    int nimg;         // images of this launch; the last group is padded with zero components up to V
     int Rproc;        // rows that get a thread: R, or ceil(R/2) under mirror pairing
     int padl, pitch;
     int a_begin, a_end;
@@ -63,9 +66,23 @@ struct BpEpiStore {
                                                const float (&val)[V]) const {
         const size_t img = (size_t)p.R * p.C;
 #pragma unroll
-        for (int i = 0; i < V; ++i) vol[((size_t)g * V + i) * img + (size_t)row * p.C + col] = scale * val[i];
+        for (int i = 0; i < V; ++i)
+            if (g * V + i < p.nimg) vol[((size_t)g * V + i) * img + (size_t)row * p.C + col] = scale * val[i];
     }
 };
+
+// Of a consumer thread's 2 columns x BP_RPT/2 vertically adjacent pixel pairs, how many share their taps (bp_kernel:
+// shared_pair).  A shared pair trades one LDS.128 (4 shared-memory wavefronts) for 8 selects.  Without sharing the
+// float4 kernel is wavefront-bound (ncu: l1tex 97.6 %, issue 63 %, 27.5 ms at 2048^2 x 1800 x 16 images); with all
+// four pairs shared, the lower pixel located from the upper one and the FMAs packed (FFMA2) it runs at l1tex 89 %,
+// issue 71 %, 23.2 ms (2 / 3 / 4 shared pairs: 24.8 / 23.5 / 23.2 ms).  The float2 and float kernels (one or two
+// images) are issue-bound to begin with -- sharing costs them 7-12 % -- and keep separate taps.
+#ifndef WT_BP_NSHARE
+#define WT_BP_NSHARE 4
+#endif
+template <int V> struct BpShare { static constexpr int value = V >= 4 ? WT_BP_NSHARE : 0; };
+// tile row of a consumer thread's r-th pixel row: vertically adjacent pairs 2*warp + {0, 1}, then 16 rows further down
+__host__ __device__ constexpr int bp_row_of(int warp, int r) { return 2 * warp + 16 * (r >> 1) + (r & 1); }
 
 template <int V>
 struct BpSmem {
@@ -138,13 +155,13 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         return;
     }
 
-    // this thread's pixels: columns lane, lane+32; rows warp, warp+8, warp+16, warp+24 (clamped into the
-    // real tile so that every smem index stays inside the staged segment; clamped results are dropped)
+    // this thread's pixels: columns lane, lane+32; rows in vertically adjacent pairs 2*warp + 16*j + {0, 1} (clamped
+    // into the real tile so that every smem index stays inside the staged segment; clamped results are dropped)
     float jc[2], ir[BP_RPT];
 #pragma unroll
     for (int c = 0; c < 2; ++c) jc[c] = (float)min(lane + 32 * c, tw - 1);
 #pragma unroll
-    for (int r = 0; r < BP_RPT; ++r) ir[r] = (float)min(warp + 8 * r, th - 1);
+    for (int r = 0; r < BP_RPT; ++r) ir[r] = (float)min(bp_row_of(warp, r), th - 1);
 
     constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
     constexpr int MAGIC_BITS = 0x4B400000;
@@ -156,32 +173,78 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[r][c][i] = 0.0f;
 
+    // One pixel: cell and fraction from the magic-number rounding, two taps, V FMAs each.
+    auto locate = [&](float ds, int &idx, float &f) {
+        const float t = ds + MAGIC;            // round(d* - 1/2) = floor(d*) (ties: the extra tap has weight 0)
+        f = ds - (t - MAGIC);                  // frac(d*) - 1/2
+        idx = __float_as_int(t) - MAGIC_BITS;
+    };
+    auto single = [&](float ds, const float4 &c4, float bw, const VecT *seg, float (&a)[V]) {
+        int idx;
+        float f;
+        locate(ds, idx, f);
+        const float w0 = fmaxf(0.0f, fmaf(-bw, f, c4.w)), w1 = fmaxf(0.0f, fmaf(bw, f, c4.w));
+        float v0[V], v1[V];
+        unpack<V>(seg[idx], v0);
+        unpack<V>(seg[idx + 1], v1);
+        tap_pair_fma<V>(w0, v0, w1, v1, a);
+    };
+    // A vertically adjacent pixel pair with shared taps (float4 kernels).  The upper pixel is located as `single`
+    // does; the lower one sits drow (|drow| <= 1) detectors further, so its cell is the same one or the next one in
+    // the direction of drow and its fraction follows with one add and one compare -- no second round trip through the
+    // magic number, no dependent address.  The four taps of the pair lie on three consecutive detectors: 3 LDS
+    // instead of 4 (shared-memory wavefronts are what bounds this kernel), the lower pixel's taps picked by select.
+    // POS = sign of drow, uniform per angle.
+    auto shared_pair = [&](auto pos_tag, float ds, const float4 &c4, float bw, const VecT *seg, float (&a0)[V],
+                           float (&a1)[V]) {
+        constexpr bool POS = decltype(pos_tag)::value;
+        int idx;
+        float f0;
+        locate(ds, idx, f0);
+        const float g = f0 + c4.y;
+        const bool moved = POS ? (g >= 0.5f) : (g < -0.5f);
+        const float f1 = moved ? (POS ? g - 1.0f : g + 1.0f) : g;
+        const float w00 = fmaxf(0.0f, fmaf(-bw, f0, c4.w)), w01 = fmaxf(0.0f, fmaf(bw, f0, c4.w));
+        const float w10 = fmaxf(0.0f, fmaf(-bw, f1, c4.w)), w11 = fmaxf(0.0f, fmaf(bw, f1, c4.w));
+        float v0[V], v1[V], vx[V], lo[V], hi[V];
+        unpack<V>(seg[idx], v0);
+        unpack<V>(seg[idx + 1], v1);
+        unpack<V>(seg[POS ? idx + 2 : idx - 1], vx);
+        tap_pair_fma<V>(w00, v0, w01, v1, a0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            lo[i] = POS ? (moved ? v1[i] : v0[i]) : (moved ? vx[i] : v0[i]);
+            hi[i] = POS ? (moved ? vx[i] : v1[i]) : (moved ? v0[i] : v1[i]);
+        }
+        tap_pair_fma<V>(w10, lo, w11, hi, a1);
+    };
+    auto one_angle = [&](auto pos_tag, const float4 &c4, float bw, const VecT *seg) {
+#pragma unroll
+        for (int j = 0; j < BP_RPT / 2; ++j) {
+            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float ds0 = fmaf(jc[c], c4.x, dr0);
+                if (2 * j + c < BpShare<V>::value) {
+                    shared_pair(pos_tag, ds0, c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
+                } else {
+                    single(ds0, c4, bw, seg, acc[2 * j][c]);
+                    single(fmaf(jc[c], c4.x, fmaf(ir[2 * j + 1], c4.y, c4.z)), c4, bw, seg, acc[2 * j + 1][c]);
+                }
+            }
+        }
+    };
+
     for (int blk = 0; blk < nblk; ++blk) {
         const int s = blk % BP_STAGES;
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
             const float4 c4 = sm.cst[s][k];
-            const float2 c2 = sm.cst2[s][k];
+            const float bw = sm.cst2[s][k].x;
             const VecT *seg = &sm.seg[s][k][0];
-#pragma unroll
-            for (int r = 0; r < BP_RPT; ++r) {
-                const float dr = fmaf(ir[r], c4.y, c4.z);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float ds = fmaf(jc[c], c4.x, dr);
-                    const float t = ds + MAGIC;            // round(d* - 1/2) = floor(d*) (ties: the extra tap has weight 0)
-                    const float f = ds - (t - MAGIC);      // frac(d*) - 1/2
-                    const int idx = __float_as_int(t) - MAGIC_BITS;
-                    const float w0 = fmaxf(0.0f, fmaf(-c2.x, f, c4.w));
-                    const float w1 = fmaxf(0.0f, fmaf(c2.x, f, c4.w));
-                    float v0[V], v1[V];
-                    unpack<V>(seg[idx], v0);
-                    unpack<V>(seg[idx + 1], v1);
-#pragma unroll
-                    for (int i = 0; i < V; ++i) acc[r][c][i] = fmaf(w0, v0[i], fmaf(w1, v1[i], acc[r][c][i]));
-                }
-            }
+            if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), c4, bw, seg);
+            else one_angle(std::false_type(), c4, bw, seg);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s
@@ -189,7 +252,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
 
 #pragma unroll
     for (int r = 0; r < BP_RPT; ++r) {
-        const int row = row0 + warp + 8 * r;
+        const int row = row0 + bp_row_of(warp, r);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int col = col0 + lane + 32 * c;

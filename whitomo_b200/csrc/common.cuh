@@ -112,6 +112,26 @@ template <> __device__ __forceinline__ float4 pack<4>(const float (&v)[4]) {
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// a[i] = fma(w0, v0[i], fma(w1, v1[i], a[i])) for the V interleaved images of one tap pair.  With four images the
+// two halves go through the packed FFMA2 of sm_100 (two fp32 FMAs per issue slot, each rounded like a scalar fma, so
+// the result bits are those of the scalar form): K1 and K2 spend half of their issue slots on these FMAs.
+#ifndef WT_FFMA2
+#define WT_FFMA2 1
+#endif
+template <int V>
+__device__ __forceinline__ void tap_pair_fma(float w0, const float (&v0)[V], float w1, const float (&v1)[V], float (&a)[V]) {
+    if constexpr (V == 4 && WT_FFMA2) {
+        const float2 W0 = make_float2(w0, w0), W1 = make_float2(w1, w1);
+        float2 lo = make_float2(a[0], a[1]), hi = make_float2(a[2], a[3]);
+        lo = __ffma2_rn(W0, make_float2(v0[0], v0[1]), __ffma2_rn(W1, make_float2(v1[0], v1[1]), lo));
+        hi = __ffma2_rn(W0, make_float2(v0[2], v0[3]), __ffma2_rn(W1, make_float2(v1[2], v1[3]), hi));
+        a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = fmaf(w0, v0[i], fmaf(w1, v1[i], a[i]));
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

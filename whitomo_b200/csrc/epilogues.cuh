@@ -19,6 +19,7 @@ struct FpEpiSirtResidual {
         const float rs = __ldg(raysum + r);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            if (g * V + i >= p.nimg) continue;       // padding component of the last group
             const size_t o = ((size_t)g * V + i) * plane + r;
             const float diff = __ldg(meas + o) - val[i];
             out[o] = rs > 0.000001f ? diff / rs : 0.0f;
@@ -36,6 +37,7 @@ struct BpEpiSirtUpdate {
         const float cs = __ldg(pixsum + px);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            if (g * V + i >= p.nimg) continue;       // padding component of the last group
             const size_t o = ((size_t)g * V + i) * img + px;
             vol[o] += cs > 0.000001f ? val[i] / cs : 0.0f;
         }
@@ -77,8 +79,9 @@ struct FpEpiWhite {
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
+            const bool real = (g * SPG + sl) * K < p.nimg;      // else: padding slice of the last group
             float q2 = 0.0f;
-            if (valid) {
+            if (valid && real) {
                 float I = 0.0f, mu[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) mu[k] = 0.0f;
@@ -106,7 +109,7 @@ struct FpEpiWhite {
         }
         if (partial) {
             __syncthreads();
-            if (tid < SPG) {
+            if (tid < SPG && (g * SPG + tid) * K < p.nimg) {
                 float s = 0.0f;
 #pragma unroll
                 for (int w = 0; w < FP_BLOCK / 32; ++w) s += red[tid][w];
@@ -139,7 +142,7 @@ struct FpEpiMar {
         for (int i = 0; i < V; ++i) {
             const size_t im = (size_t)g * V + i;
             float cost = 0.0f, phi = 0.0f, bad = 0.0f;
-            if (valid) {
+            if (valid && g * V + i < p.nimg) {
                 const size_t o = im * plane + r;
                 const float P = val[i];
                 float uu;
@@ -163,7 +166,7 @@ struct FpEpiMar {
         }
         if (partial) {
             __syncthreads();
-            if (tid < 3 * V) {
+            if (tid < 3 * V && g * V + tid % V < p.nimg) {
                 const int q = tid / V, i = tid % V;
                 float s = 0.0f;
 #pragma unroll

@@ -52,7 +52,7 @@ __host__ __device__ inline int fp_pitch(int npos) {
 // run through the V = 2 / V = 4 kernels with half the rays and shared index arithmetic (DESIGN.md "mirror pairing").
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__ vol, float *__restrict__ vn,
-                                                       float *__restrict__ vt, int R, int C) {
+                                                       float *__restrict__ vt, int R, int C, int nimg) {
     static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
     constexpr int V0 = MIRROR ? V / 2 : V;   // images per group
@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
         const bool in = (r >= 0 && r < R && c >= 0 && c < C);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            if (MIRROR && i >= V0) v[i] = in ? __ldg(src + (i - V0) * img + (size_t)(R - 1 - r) * C + (C - 1 - c)) : 0.0f;
-            else v[i] = in ? __ldg(src + i * img + (size_t)r * C + c) : 0.0f;
+            // components past the last image (padding of the last group) are zero
+            const bool real = g * V0 + (MIRROR && i >= V0 ? i - V0 : i) < nimg;
+            if (MIRROR && i >= V0) v[i] = in && real ? __ldg(src + (i - V0) * img + (size_t)(R - 1 - r) * C + (C - 1 - c)) : 0.0f;
+            else v[i] = in && real ? __ldg(src + i * img + (size_t)r * C + c) : 0.0f;
             tile[i][rr][tx] = v[i];
         }
         if (r >= 0 && r < R && c + VPAD < Cp)
@@ -93,11 +95,11 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
 }
 
 template <int V, bool MIRROR = false>
-inline void launch_pack_vol(const float *vol, float *vn, float *vt, int R, int C, int groups, cudaStream_t st) {
+inline void launch_pack_vol(const float *vol, float *vn, float *vt, int R, int C, int groups, int nimg, cudaStream_t st) {
     // the tile grid covers the padded extents of both copies (pitch may exceed npos + 2*VPAD for tiny volumes)
     const int ext_c = max(fp_pitch(C), C + 2 * VPAD), ext_r = max(fp_pitch(R), R + 2 * VPAD);
     dim3 grid((ext_c + 31) / 32, (ext_r + 31) / 32, groups);
-    pack_vol_kernel<V, MIRROR><<<grid, dim3(32, 8), 0, st>>>(vol, vn, vt, R, C);
+    pack_vol_kernel<V, MIRROR><<<grid, dim3(32, 8), 0, st>>>(vol, vn, vt, R, C, nimg);
 }
 
 // ---- projector ------------------------------------------------------------------------------------
@@ -112,6 +114,7 @@ struct FpParams {
     const FpTile *tiles;
     int ntiles;
     int R, C, D, A;
+    int nimg;          // images of this launch; the last group is padded with zero components up to V
     int Dproc;         // detectors that get a thread: D, or ceil(D/2) under mirror pairing
     int a_begin, a_end;
     // CTA launch order (see fp_block): tiles grouped into phases (one per orientation)
@@ -164,7 +167,8 @@ struct FpEpiStore {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D;
 #pragma unroll
-        for (int i = 0; i < V; ++i) sino[((size_t)g * V + i) * plane + (size_t)a * p.D + d] = val[i];
+        for (int i = 0; i < V; ++i)
+            if (g * V + i < p.nimg) sino[((size_t)g * V + i) * plane + (size_t)a * p.D + d] = val[i];
     }
 };
 
@@ -333,8 +337,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
                     unpack<V>(row[idx], v0);
                     unpack<V>(row[idx + 1], v1);
                     const float w0 = 1.0f - off;
-#pragma unroll
-                    for (int i = 0; i < V; ++i) acc[i] = fmaf(off, v1[i], fmaf(w0, v0[i], acc[i]));
+                    tap_pair_fma<V>(off, v1, w0, v0, acc);
                     cr += delta;
                     row += FP_W;
                 }

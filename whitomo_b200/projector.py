@@ -79,7 +79,7 @@ class Projector(object):
                                                 self.angles.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                                                 self.nangles, ctypes.byref(h)))
         self.handle = h
-        self._ws = None
+        self._ws = {}
 
     def __del__(self):
         try:
@@ -99,10 +99,14 @@ class Projector(object):
         return (self.nangles, self.ndet)
 
     def _workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+        """scratch for the packed copies and partial sums, one buffer per CUDA stream: calls issued on different
+        streams may overlap on the device, calls on one stream are ordered (so is the allocator's reuse on growth)"""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self._ws.pop(key, None)
+            ws = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return ws
 
     def _as_images(self, t, shape):
         """accept (..., *shape) float32 CUDA tensors; return (contiguous (n, *shape) view, leading dims)"""
