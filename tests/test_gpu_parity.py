@@ -75,7 +75,7 @@ def test_special_angles(eng):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8])
 def test_image_batches_cover_all_interleave_widths(eng, n):
-    """n images are processed as groups of 4 / 2 / 1 interleaved images; every image must equal its solo result"""
+    """n images are processed as float4 groups (the last one padded), or as one float2 / float group; every image must equal its solo result"""
     Projector, _ = eng
     r, c, d, a = 40, 56, 75, 24
     g = oracle.Geometry(r, c, d, np.linspace(0, np.pi, a))

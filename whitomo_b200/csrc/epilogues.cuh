@@ -68,14 +68,32 @@ struct FpEpiWhite {
         const int nblocks = p.ndblk * p.ntiles * npass;
         const int bid = pass * p.ndblk * p.ntiles + fp_block_id(p);
         const int tid = threadIdx.x;
-        // spectrum tables -> shared memory (the projector's staging buffers are idle now): broadcast LDS in the bin loop
-        const int ntab = (K + 1) * E;
-        const bool in_smem = ntab * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);
+        // spectrum tables -> shared memory (the projector's staging buffers are idle now), interleaved per bin
+        // {s_e w_e, a_0e, .., a_(K-1)e}: one broadcast LDS.64 / LDS.128 per bin in the loop below instead of K + 1 scalar ones
+        constexpr int TW = (K + 1 <= 2) ? 2 : 4;
+        static_assert(K + 1 <= TW, "table row wider than a float4");
+        const bool in_smem = E * TW * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);
         __syncthreads();
         if (in_smem)
-            for (int i = tid; i < ntab; i += FP_BLOCK) scratch[i] = __ldg(tab + i);
+            for (int i = tid; i < (K + 1) * E; i += FP_BLOCK) {
+                const int j = i / E, e = i - j * E;
+                scratch[e * TW + j] = __ldg(tab + i);
+            }
         __syncthreads();
-        const float *tb = in_smem ? scratch : tab;
+        auto bin = [&](int e, float &sw, float (&ab)[K]) {
+            if (in_smem) {
+                float row[TW];
+                if constexpr (TW == 2) unpack<2>(reinterpret_cast<const float2 *>(scratch)[e], row);
+                else unpack<4>(reinterpret_cast<const float4 *>(scratch)[e], row);
+                sw = row[0];
+#pragma unroll
+                for (int k = 0; k < K; ++k) ab[k] = row[k + 1];
+            } else {
+                sw = __ldg(tab + e);
+#pragma unroll
+                for (int k = 0; k < K; ++k) ab[k] = __ldg(tab + (k + 1) * E + e);
+            }
+        };
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
@@ -86,13 +104,14 @@ struct FpEpiWhite {
 #pragma unroll
                 for (int k = 0; k < K; ++k) mu[k] = 0.0f;
                 for (int e = 0; e < E; ++e) {
-                    float arg = 0.0f;
+                    float sw, ab[K], arg = 0.0f;
+                    bin(e, sw, ab);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) arg = fmaf(tb[(k + 1) * E + e], val[sl * K + k], arg);
-                    const float t = tb[e] * exp2f(-arg);     // tables are pre-scaled by log2(e): one MUFU.EX2
+                    for (int k = 0; k < K; ++k) arg = fmaf(ab[k], val[sl * K + k], arg);
+                    const float t = sw * exp2f(-arg);        // tables are pre-scaled by log2(e): one MUFU.EX2
                     I += t;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, tb[(k + 1) * E + e], mu[k]);
+                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, ab[k], mu[k]);
                 }
                 const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
                 if (inten) inten[slice * plane + r] = I;
