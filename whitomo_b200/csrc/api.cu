@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "bp.cuh"
@@ -145,6 +146,10 @@ struct HFpMar : FpEpiMar { static constexpr int kMult = 1; };
 template <int K> struct HFpWhite : FpEpiWhite<K> { static constexpr int kMult = K; };
 typedef BpEpiStore HBpStore;
 typedef BpEpiSirtUpdate HBpSirt;
+
+// constant-memory slots of the spectrum tables, per device
+static std::mutex g_slot_mutex;
+static unsigned g_slots_used[64] = {};   // bit i of entry d: slot i is taken on device d
 
 }  // namespace wt
 
@@ -421,8 +426,20 @@ int wt_spectrum_create(int n_elements, int n_bins, const double *source, const d
         for (int e = 0; e < n_bins; ++e) tab[(size_t)(k + 1) * n_bins + e] = (float)(pixel_size * absorptions[(size_t)k * n_bins + e] * 1.4426950408889634);
     wt_spectrum *s = new wt_spectrum();
     s->K = n_elements; s->E = n_bins; s->d_tab = nullptr;
-    cudaError_t e = cudaMalloc(&s->d_tab, tab.size() * sizeof(float));
+    s->cslot = -1; s->device = 0;
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_tab, tab.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(s->d_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && tab.size() <= (size_t)WT_CTAB) {
+        std::lock_guard<std::mutex> lock(g_slot_mutex);
+        unsigned &used = g_slots_used[s->device & 63];
+        for (int i = 0; i < WT_CSLOTS && s->cslot < 0; ++i)
+            if (!(used & (1u << i))) { used |= 1u << i; s->cslot = i; }
+        // a kernel of a destroyed spectrum may still be reading the slot on some stream: creation is set-up time, wait
+        if (s->cslot >= 0) e = cudaDeviceSynchronize();
+        if (s->cslot >= 0 && e == cudaSuccess)
+            e = cudaMemcpyToSymbol(c_spectrum_tab, tab.data(), tab.size() * sizeof(float), (size_t)s->cslot * WT_CTAB * sizeof(float));
+    }
     if (e != cudaSuccess) { wt_spectrum_destroy(s); return cuda_fail(e, "wt_spectrum_create"); }
     *out = s;
     return WT_OK;
@@ -431,6 +448,10 @@ int wt_spectrum_create(int n_elements, int n_bins, const double *source, const d
 void wt_spectrum_destroy(wt_spectrum *s) {
     if (!s) return;
     if (s->d_tab) cudaFree(s->d_tab);
+    if (s->cslot >= 0) {
+        std::lock_guard<std::mutex> lock(g_slot_mutex);
+        g_slots_used[s->device & 63] &= ~(1u << s->cslot);
+    }
     delete s;
 }
 
@@ -455,11 +476,11 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
         nb = fp_blocks(g);
         int rc;
         if (K == 1) {
-            HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
+            HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = intensity; e.qmu = qmu;
             e.partial = loss ? partial : nullptr;
             rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         } else {
-            HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.meas = meas; e.inten = intensity; e.qmu = qmu;
+            HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = intensity; e.qmu = qmu;
             e.partial = loss ? partial : nullptr;
             rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         }

@@ -79,6 +79,8 @@ struct wt_geom {
 struct wt_spectrum {
     int K, E;
     float *d_tab;  // [E] s_e*w_e, then K rows [E] of pix*ea[k,e]*log2(e)  (the kernels use exp2)
+    int cslot;     // slot of the __constant__ table pool on `device`, or -1 (epilogues.cuh: c_spectrum_tab)
+    int device;
 };
 
 namespace wt {

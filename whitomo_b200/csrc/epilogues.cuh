@@ -49,10 +49,24 @@ __global__ void fill_kernel(float *p, size_t n, float v) {
 }
 
 // ---- white-beam model fused into the projector (src/white_projection.py:86-98,116-139) -----------------
+#ifndef WT_CTAB
+#define WT_CTAB 384   // floats per constant-memory slot (E <= 128 at K = 2)
+#endif
+constexpr int WT_CSLOTS = 16;   // live spectra with a constant-memory slot (per device)
+__constant__ float c_spectrum_tab[WT_CSLOTS * WT_CTAB];
+
+// exp2 for the bin loop: one MUFU.EX2, results below the normal range flushed to zero (such a bin contributes
+// nothing to a float32 sum of 64 terms of order one)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // A group of V interleaved images holds V/K slices x K elements (image index = slice*K + k).
 template <int K>
 struct FpEpiWhite {
     const float *tab;   // [E] s_e*w_e, then K x [E] pix*ea[k][e]*log2(e)
+    int cslot;          // slot of c_spectrum_tab holding the same table, or -1
     int E;
     const float *meas;  // (S, A, D) or null
     float *inten;       // (S, A, D) or null
@@ -68,51 +82,47 @@ struct FpEpiWhite {
         const int nblocks = p.ndblk * p.ntiles * npass;
         const int bid = pass * p.ndblk * p.ntiles + fp_block_id(p);
         const int tid = threadIdx.x;
-        // spectrum tables -> shared memory (the projector's staging buffers are idle now), interleaved per bin
-        // {s_e w_e, a_0e, .., a_(K-1)e}: one broadcast LDS.64 / LDS.128 per bin in the loop below instead of K + 1 scalar ones
-        constexpr int TW = (K + 1 <= 2) ? 2 : 4;
-        static_assert(K + 1 <= TW, "table row wider than a float4");
-        const bool in_smem = E * TW * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);
-        __syncthreads();
-        if (in_smem)
-            for (int i = tid; i < (K + 1) * E; i += FP_BLOCK) {
-                const int j = i / E, e = i - j * E;
-                scratch[e * TW + j] = __ldg(tab + i);
-            }
-        __syncthreads();
-        auto bin = [&](int e, float &sw, float (&ab)[K]) {
-            if (in_smem) {
-                float row[TW];
-                if constexpr (TW == 2) unpack<2>(reinterpret_cast<const float2 *>(scratch)[e], row);
-                else unpack<4>(reinterpret_cast<const float4 *>(scratch)[e], row);
-                sw = row[0];
+        // Spectrum tables.  A spectrum of up to WT_CTAB floats owns a slot of __constant__ memory (filled once, at
+        // wt_spectrum_create): the bin loop reads it through the constant cache (LDC with a warp-uniform index) and
+        // costs no shared-memory wavefronts -- K + 1 broadcast LDS per bin were 3.5 % of this LSU-bound kernel's
+        // wavefronts (a float4 row per bin was worse: a broadcast LDS.128 still takes four).  Larger tables, or more
+        // live spectra than slots, use the idle staging buffers, or stay in global memory.
+        const int ntab = (K + 1) * E;
+        const bool in_const = cslot >= 0;
+        const bool in_smem = !in_const && ntab * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);
+        if (!in_const) {
+            __syncthreads();
+            if (in_smem)
+                for (int i = tid; i < ntab; i += FP_BLOCK) scratch[i] = __ldg(tab + i);
+            __syncthreads();
+        }
+        const float *tb = in_smem ? scratch : tab;
+        // the bin loop, once per table source so that the constant-memory version compiles to LDC (a pointer chosen at
+        // run time would turn both into generic loads)
+        auto bins = [&](auto table, const float *P, float &I, float (&mu)[K]) {
+            for (int e = 0; e < E; ++e) {
+                const float sw = table(e);
+                float ab[K], arg = 0.0f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) ab[k] = row[k + 1];
-            } else {
-                sw = __ldg(tab + e);
+                for (int k = 0; k < K; ++k) { ab[k] = table((k + 1) * E + e); arg = fmaf(ab[k], P[k], arg); }
+                const float t = sw * ex2_ftz(-arg);           // tables are pre-scaled by log2(e): one MUFU.EX2
+                I += t;
 #pragma unroll
-                for (int k = 0; k < K; ++k) ab[k] = __ldg(tab + (k + 1) * E + e);
+                for (int k = 0; k < K; ++k) mu[k] = fmaf(t, ab[k], mu[k]);
             }
         };
+        const int cbase = in_const ? cslot * WT_CTAB : 0;
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
             const bool real = (g * SPG + sl) * K < p.nimg;      // else: padding slice of the last group
             float q2 = 0.0f;
             if (valid && real) {
-                float I = 0.0f, mu[K];
+                float I = 0.0f, mu[K], P[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) mu[k] = 0.0f;
-                for (int e = 0; e < E; ++e) {
-                    float sw, ab[K], arg = 0.0f;
-                    bin(e, sw, ab);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) arg = fmaf(ab[k], val[sl * K + k], arg);
-                    const float t = sw * exp2f(-arg);        // tables are pre-scaled by log2(e): one MUFU.EX2
-                    I += t;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) mu[k] = fmaf(t, ab[k], mu[k]);
-                }
+                for (int k = 0; k < K; ++k) { mu[k] = 0.0f; P[k] = val[sl * K + k]; }
+                if (in_const) bins([&](int i) { return c_spectrum_tab[cbase + i]; }, P, I, mu);
+                else bins([&](int i) { return tb[i]; }, P, I, mu);
                 const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
                 if (inten) inten[slice * plane + r] = I;
                 if (qmu) {
