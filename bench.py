@@ -22,6 +22,8 @@ import time
 
 import numpy as np
 
+_REAL_STDOUT = sys.stdout   # main() re-points file descriptor 1 at stderr and keeps the real stdout here
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -174,7 +176,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "barrier_iters_per_s": 1.0 / t * (n_s / float(A)),
-    }), flush=True)
+    }), file=_REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -392,7 +394,7 @@ def run_gpu(args):
     out["roofline"], out["roofline_other"] = (r_fp, r_bp) if t_fp >= t_bp else (r_bp, r_fp)    # dominant kernel first
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_block()
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -406,6 +408,13 @@ def main():
     ap.add_argument("--slices", type=int, default=8, help="resident slices per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout
+    # when NCCL_DEBUG is set), so file descriptor 1 points at stderr while the benchmark runs and the JSON line goes
+    # to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
