@@ -57,6 +57,28 @@ def main():
     t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # where the time goes on each rank: local FP rows, local partial BP, the all-reduce
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    r_loc = sp.fp(x)
+    part = P.bp(r_loc, angle_range=sp.range)
+    parts = torch.tensor([timed(lambda: sp.fp(x)), timed(lambda: P.bp(r_loc, angle_range=sp.range)),
+                          timed(lambda: sp._allreduce(part))], device=dev, dtype=torch.float64)
+    allparts = [torch.zeros_like(parts) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allparts, parts)
+    else:
+        allparts = [parts]
     # single-GPU time of the same iteration for reference
     e0.record()
     for _ in range(reps):
@@ -68,7 +90,10 @@ def main():
         print(json.dumps({"config": "C5-style angle split", "N": n, "A": na, "ranks": world, "range_rank0": [a0, a1],
                           "fp_rows_bitwise_equal": ok_fp, "bp_rel_l2_vs_single_gpu": err_bp,
                           "ms_per_iteration_split": float(t.item()), "ms_per_iteration_single_gpu": t1,
-                          "gups_split": 2.0 * n * n * na / (float(t.item()) * 1e-3) / 1e9}), flush=True)
+                          "gups_split": 2.0 * n * n * na / (float(t.item()) * 1e-3) / 1e9,
+                          "per_rank_ms_fp_bp_allreduce": [[round(v, 3) for v in q.tolist()] for q in allparts],
+                          "angle_ranges": [list(r) for r in __import__("whitomo_b200.distributed", fromlist=["x"]).angle_ranges(na, world)]}),
+              flush=True)
     if world > 1:
         dist.destroy_process_group()
 
