@@ -50,6 +50,21 @@ def test_angles_bounds_and_nptxt(tmp_path):
     assert np.array_equal(teeth_io.loadtxt(p), np.loadtxt(p)) and np.allclose(teeth_io.loadtxt(p), x, rtol=0, atol=1e-15)
 
 
+def test_normalize_data_numpy_and_tensor_agree():
+    rng = np.random.default_rng(2)
+    dark = rng.uniform(90, 110, (3, 8, 8))
+    empty = rng.uniform(5000, 5200, (3, 8, 8))
+    data = rng.uniform(50, 5000, (5, 8, 8))
+    avg_dark = dark.mean()
+    i0_ref = (empty - avg_dark).mean()
+    ref = (np.log(i0_ref + 1e-3) - np.log(np.maximum(data, avg_dark) - avg_dark + 1e-3)) / 2.0   # preproc_data.py:29-36
+    r_np, i0 = teeth_io.normalize_data(data.copy(), dark, empty, 2.0)
+    assert np.allclose(r_np, ref, rtol=0, atol=1e-12) and np.isclose(i0, i0_ref)
+    r_t, i0_t = teeth_io.normalize_data(torch.from_numpy(data.copy()), dark, empty, 2.0)
+    assert np.allclose(r_t.numpy(), ref, rtol=0, atol=1e-9) and np.isclose(i0_t, i0_ref)
+    assert r_np.min() >= -1e-12 + np.log(i0_ref + 1e-3) / 2.0 - np.log(5000 - avg_dark + 1e-3) / 2.0
+
+
 def test_hdf5_reader_fails_loudly_without_h5py(tmp_path):
     try:
         import h5py  # noqa: F401

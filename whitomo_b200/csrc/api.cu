@@ -74,7 +74,8 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
     p.a_begin = a_begin; p.a_end = a_end;
     p.order = g->d_order; p.nphase = g->nphase;
-    { const char *e = getenv("WT_FP_ORDER"); if (e && !strcmp(e, "tile")) p.nphase = 0; }
+    static const bool tile_major = [] { const char *e = getenv("WT_FP_ORDER"); return e && !strcmp(e, "tile"); }();
+    if (tile_major) p.nphase = 0;   // A/B measurements only
     for (int i = 0; i <= FP_MAX_PHASES; ++i) p.phase_start[i] = g->phase_start[i];
     p.ndblk = 0;   // set by launch_fp from Dproc
     p.nimg = n;

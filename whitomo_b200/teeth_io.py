@@ -2,6 +2,7 @@
 
   read_data_from_hdf5   teeth_recon/teeth_io.py:47-54   h5 dataset 'sinogram'[angle, det, slice], 0.5 degree steps
   check_bounds          teeth_recon/teeth_recon.py:64-71  clip the line integrals to [minbound, maxbound] + masks
+  normalize_data        teeth_recon/preproc_data.py:29-36  dark / flat-field correction and -log of raw counts
   slice_stack           the slice-major reader that feeds the C4 pipeline from such a cube
   savetxt / loadtxt     the `.nptxt` dumps of src/barrier_method_gogo.py:156-157 (np.savetxt of one element map)
 
@@ -88,6 +89,21 @@ def check_bounds(r, maxbound, minbound):
     r[M] = maxbound
     r[m] = minbound
     return r, M, m
+
+
+def normalize_data(data, dark, empty, pix_size):
+    """(line integrals, I0) from raw counts -- teeth_recon/preproc_data.py:29-36:  I0 = mean(empty - mean(dark));
+    counts below the dark level are raised to it (in place, like the reference);
+    r = (log(I0 + 1e-3) - log(data - mean(dark) + 1e-3)) / pix_size.  numpy arrays or (device) tensors."""
+    if isinstance(data, torch.Tensor):
+        avg_dark = torch.as_tensor(dark, dtype=torch.float64).mean().item()
+        i0 = (torch.as_tensor(empty, dtype=torch.float64) - avg_dark).mean().item()
+        data.clamp_(min=avg_dark)
+        return (float(np.log(i0 + 1e-3)) - torch.log(data - avg_dark + 1e-3)) / pix_size, i0
+    avg_dark = np.mean(dark)
+    i0 = np.mean(empty - avg_dark)
+    data[data < avg_dark] = avg_dark
+    return (np.log(i0 + 1e-3) - np.log(data - avg_dark + 1e-3)) / pix_size, i0
 
 
 def savetxt(path, x):
