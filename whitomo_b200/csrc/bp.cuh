@@ -72,11 +72,12 @@ struct BpEpiStore {
 };
 
 // Of a consumer thread's 2 columns x BP_RPT/2 vertically adjacent pixel pairs, how many share their taps (bp_kernel:
-// shared_pair).  A shared pair trades one LDS.128 (4 shared-memory wavefronts) for 8 selects.  Without sharing the
-// float4 kernel is wavefront-bound (ncu: l1tex 97.6 %, issue 63 %, 27.5 ms at 2048^2 x 1800 x 16 images); with all
-// four pairs shared, the lower pixel located from the upper one and the FMAs packed (FFMA2) it runs at l1tex 89 %,
-// issue 71 %, 23.2 ms (2 / 3 / 4 shared pairs: 24.8 / 23.5 / 23.2 ms).  The float2 and float kernels (one or two
-// images) are issue-bound to begin with -- sharing costs them 7-12 % -- and keep separate taps.
+// shared_pair).  A shared pair trades one LDS.128 (4 shared-memory wavefronts) for a few scalar instructions.  Without
+// sharing the float4 kernel is wavefront-bound (ncu: l1tex 97.6 %, issue 63 %, 27.5 ms at 2048^2 x 1800 x 16 images);
+// with all four pairs shared, the lower pixel located from the upper one, the FMAs packed (FFMA2) and three weights
+// on three taps it takes 22.0 ms (with selects on the taps instead: 23.2 ms at l1tex 89 %, issue 71 %; 2 / 3 / 4
+// shared pairs: 24.8 / 23.5 / 23.2 ms).  The float2 and float kernels (one or two images) are issue-bound to begin
+// with -- sharing costs them 7-12 % -- and keep separate taps.
 #ifndef WT_BP_NSHARE
 #define WT_BP_NSHARE 4
 #endif
@@ -193,7 +194,9 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     // does; the lower one sits drow (|drow| <= 1) detectors further, so its cell is the same one or the next one in
     // the direction of drow and its fraction follows with one add and one compare -- no second round trip through the
     // magic number, no dependent address.  The four taps of the pair lie on three consecutive detectors: 3 LDS
-    // instead of 4 (shared-memory wavefronts are what bounds this kernel), the lower pixel's taps picked by select.
+    // instead of 4 (shared-memory wavefronts are what bounds this kernel).  The lower pixel puts three weights on the
+    // three taps, (w0, w1, 0) or (0, w0, w1) depending on its cell: 3 selects on scalars instead of 2 V selects on
+    // taps, and fma(0, tap, acc) leaves acc untouched, so the bits are those of the two-tap form.
     // POS = sign of drow, uniform per angle.
     auto shared_pair = [&](auto pos_tag, float ds, const float4 &c4, float bw, const VecT *seg, float (&a0)[V],
                            float (&a1)[V]) {
@@ -206,17 +209,17 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         const float f1 = moved ? (POS ? g - 1.0f : g + 1.0f) : g;
         const float w00 = fmaxf(0.0f, fmaf(-bw, f0, c4.w)), w01 = fmaxf(0.0f, fmaf(bw, f0, c4.w));
         const float w10 = fmaxf(0.0f, fmaf(-bw, f1, c4.w)), w11 = fmaxf(0.0f, fmaf(bw, f1, c4.w));
-        float v0[V], v1[V], vx[V], lo[V], hi[V];
+        float v0[V], v1[V], vx[V];
         unpack<V>(seg[idx], v0);
         unpack<V>(seg[idx + 1], v1);
         unpack<V>(seg[POS ? idx + 2 : idx - 1], vx);
         tap_pair_fma<V>(w00, v0, w01, v1, a0);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            lo[i] = POS ? (moved ? v1[i] : v0[i]) : (moved ? vx[i] : v0[i]);
-            hi[i] = POS ? (moved ? vx[i] : v1[i]) : (moved ? v0[i] : v1[i]);
-        }
-        tap_pair_fma<V>(w10, lo, w11, hi, a1);
+        // taps in detector order: (v0, v1, vx) for POS, (vx, v0, v1) otherwise
+        const float wa = POS ? (moved ? 0.0f : w10) : (moved ? w10 : 0.0f);
+        const float wb = POS ? (moved ? w10 : w11) : (moved ? w11 : w10);
+        const float wc = POS ? (moved ? w11 : 0.0f) : (moved ? 0.0f : w11);
+        if constexpr (POS) tap_triple_fma<V>(wa, v0, wb, v1, wc, vx, a1);
+        else tap_triple_fma<V>(wa, vx, wb, v0, wc, v1, a1);
     };
     auto one_angle = [&](auto pos_tag, const float4 &c4, float bw, const VecT *seg) {
 #pragma unroll

@@ -134,6 +134,22 @@ __device__ __forceinline__ void tap_pair_fma(float w0, const float (&v0)[V], flo
     }
 }
 
+// a[i] = fma(w0, v0[i], fma(w1, v1[i], fma(w2, v2[i], a[i])))
+template <int V>
+__device__ __forceinline__ void tap_triple_fma(float w0, const float (&v0)[V], float w1, const float (&v1)[V], float w2,
+                                               const float (&v2)[V], float (&a)[V]) {
+    if constexpr (V == 4 && WT_FFMA2) {
+        const float2 W0 = make_float2(w0, w0), W1 = make_float2(w1, w1), W2 = make_float2(w2, w2);
+        float2 lo = make_float2(a[0], a[1]), hi = make_float2(a[2], a[3]);
+        lo = __ffma2_rn(W0, make_float2(v0[0], v0[1]), __ffma2_rn(W1, make_float2(v1[0], v1[1]), __ffma2_rn(W2, make_float2(v2[0], v2[1]), lo)));
+        hi = __ffma2_rn(W0, make_float2(v0[2], v0[3]), __ffma2_rn(W1, make_float2(v1[2], v1[3]), __ffma2_rn(W2, make_float2(v2[2], v2[3]), hi)));
+        a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = fmaf(w0, v0[i], fmaf(w1, v1[i], fmaf(w2, v2[i], a[i])));
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
