@@ -378,3 +378,51 @@ def test_soft_inequality_least_squares_scipy_cg_over_the_drop_in():
     xc = opt.fmin_cg(cpu_c[0], x0, cpu_c[1], maxiter=6, disp=False)
     assert rel_l2(xd, xc) < 5e-3
     assert dev_c[0](xd) < dev_c[0](x0.astype(np.float64))
+
+
+def test_stack_job_checkpoint_and_resume(golden, tmp_path, monkeypatch):
+    """every finished batch is written to the checkpoint directory; a restarted job loads what it finds (bit-identical)
+    and recomputes only what is missing or was written for other data"""
+    import os
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    grid = z["grid"]
+    P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    sp = Spectrum(z["source"] / np.sum(z["source"] * grid[:, 1]), grid[:, 1], z["ea"], float(z["pixel_size"]))
+    rng = np.random.default_rng(5)
+    S = 8
+    gts = np.stack([np.clip(z["gt"] * rng.uniform(0.5, 1.0), 0, 1) for _ in range(S)]).astype(np.float32)
+    meas = P.white_fp(sp, torch.from_numpy(gts).cuda(), want_qmu=False, want_loss=False)[0].cpu().pin_memory()
+    x0 = torch.from_numpy(np.stack([z["x0"] * rng.uniform(0.8, 1.2) for _ in range(S)]).astype(np.float32)).pin_memory()
+    p = dict(n_iter=3, n_biter=2, t0=0.1, t_step=0.5, alpha=0.3, ir_beta=0.05, max_iter=10, n_steps_without_progress=None)
+    ck = str(tmp_path / "ck")
+    ref, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, **p)
+    first, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, checkpoint=ck, **p)
+    assert torch.equal(first, ref)
+    files = sorted(f for f in os.listdir(ck) if f.endswith(".npy"))
+    assert len(files) == 3 and not [f for f in os.listdir(ck) if f.endswith(".tmp")]
+
+    calls = []
+    real = solvers.white_barrier_stack
+
+    def counting(*a, **k):
+        calls.append(a[2].shape[0])
+        return real(*a, **k)
+    monkeypatch.setattr(solvers, "white_barrier_stack", counting)
+    again, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, checkpoint=ck, **p)
+    assert torch.equal(again, ref) and calls == []                       # everything came from the files
+    os.remove(os.path.join(ck, files[1]))
+    again, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, checkpoint=ck, **p)
+    assert torch.equal(again, ref) and calls == [3]                      # only the missing batch was recomputed
+    # other parameters or other data never reuse these files
+    calls.clear()
+    p2 = dict(p, alpha=0.2)
+    other, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, checkpoint=ck, **p2)
+    assert len(calls) == 3 and not torch.equal(other, ref)
+    calls.clear()
+    meas2 = meas.clone()
+    meas2[0] *= 1.01
+    solvers.white_barrier_reconstruct(P, sp, meas2, x0, batch=3, checkpoint=ck, **p)
+    assert calls == [3]                                                   # the batch holding the changed slice

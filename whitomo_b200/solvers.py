@@ -233,7 +233,19 @@ def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t
     return x.reshape(lead + proj.vol_shape)
 
 
-def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=0, world=1, **params):
+def _checkpoint_key(proj, spectrum, meas_host, x0_host, params):
+    """what a stored batch result depends on besides its own slices' data (those are fingerprinted per batch)"""
+    import hashlib
+    import json
+    h = hashlib.sha256()
+    h.update(json.dumps({"rows": proj.rows, "cols": proj.cols, "ndet": proj.ndet, "K": spectrum.K, "E": spectrum.E,
+                         "params": {k: repr(v) for k, v in sorted(params.items())},
+                         "meas": list(meas_host.shape), "x0": list(x0_host.shape)}, sort_keys=True).encode())
+    h.update(np.ascontiguousarray(proj.angles).tobytes())
+    return h.hexdigest()[:16]
+
+
+def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=0, world=1, checkpoint=None, **params):
     """The C4 job: a stack of independent slices (host memory) reconstructed in resident batches on this rank's GPU.
 
     meas_host (S, A, D) and x0_host (S, K, N, N) are CPU tensors (pinned memory makes the copies asynchronous).  The
@@ -241,6 +253,10 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
     ``batch`` slices at a time on a copy stream while the previous batch iterates, runs ALL barrier iterations of a
     batch while it is resident (slices are independent, so nothing else ever needs to be on the device), and writes
     the result into the returned CPU tensor.  ``params`` are those of ``white_barrier_stack``.
+    ``checkpoint``: a directory.  Every finished batch is written there (one .npy per batch, named after the job key --
+    geometry, angles, spectrum size, solver parameters -- and the slice range, with a checksum of the batch's
+    measurements); a restarted call loads the batches it finds instead of recomputing them, so a stack job that
+    dies after hours resumes at the batch it was working on.  Slices are independent, so this is the whole state.
     Returns (x_host for the rank's range, (start, stop))."""
     from .distributed import shard_range
     s0, s1 = shard_range(meas_host.shape[0], rank, world)
@@ -271,16 +287,67 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
             ev.record()
         return b0, b1, m, x, ev
 
-    nxt = upload(s0) if s1 > s0 else None
-    while nxt is not None:
-        b0, b1, m, x, ev = nxt
-        nxt = upload(b1) if b1 < s1 else None            # overlaps the iterations below
+    import os
+    key = _checkpoint_key(proj, spectrum, meas_host, x0_host, params) if checkpoint else None
+    if checkpoint:
+        os.makedirs(checkpoint, exist_ok=True)
+
+    def ckpt_path(b0):
+        return os.path.join(checkpoint, "x_%s_%06d_%06d.npy" % (key, b0, nxt_of[b0]))
+
+    def fingerprint(b0):
+        # the batch's inputs: a cheap checksum (float64 sums) guards against reusing results of other data
+        m, x = meas_host[b0:nxt_of[b0]], x0_host[b0:nxt_of[b0]]
+        return np.array([float(m.double().sum()), float(x.double().sum())])
+
+    def restore(b0):
+        """finished batch from an earlier run, or None"""
+        if not checkpoint or not os.path.exists(ckpt_path(b0)):
+            return None
+        try:
+            with open(ckpt_path(b0), "rb") as f:
+                fp, arr = np.load(f), np.load(f)
+        except Exception:
+            return None                                   # truncated file of a run that died while writing
+        want = (nxt_of[b0] - b0,) + tuple(x0_host.shape[1:])
+        if arr.shape != want or not np.array_equal(fp, fingerprint(b0)):
+            return None
+        return torch.from_numpy(arr)
+
+    def store(b0, res_host):
+        tmp = ckpt_path(b0) + ".tmp"
+        with open(tmp, "wb") as f:
+            np.save(f, fingerprint(b0))
+            np.save(f, res_host.numpy())
+        os.replace(tmp, ckpt_path(b0))                    # atomic: a batch file is complete or absent
+
+    todo = []
+    for b0 in cuts[:-1]:
+        done = restore(b0)
+        if done is not None:
+            out[b0 - s0:nxt_of[b0] - s0].copy_(done)
+        else:
+            todo.append(b0)
+    pending = None                                        # (b0, event) of the batch whose download is in flight
+    nxt = upload(todo[0]) if todo else None
+    for i, b0 in enumerate(todo):
+        _, b1, m, x, ev = nxt
+        nxt = upload(todo[i + 1]) if i + 1 < len(todo) else None      # overlaps the iterations below
         main.wait_event(ev)
         m.record_stream(main)
         x.record_stream(main)
         res, _ = white_barrier_stack(proj, spectrum, m, x, **params)
         out[b0 - s0:b1 - s0].copy_(res, non_blocking=True)
+        if checkpoint:
+            if pending is not None:                       # the previous batch's download has long finished
+                pending[1].synchronize()
+                store(pending[0], out[pending[0] - s0:nxt_of[pending[0]] - s0])
+            done_ev = torch.cuda.Event()
+            done_ev.record(main)
+            pending = (b0, done_ev)
     torch.cuda.synchronize(dev)
+    if checkpoint and pending is not None:
+        store(pending[0], out[pending[0] - s0:nxt_of[pending[0]] - s0])
     return out, (s0, s1)
 
 
