@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--n-iter", type=int, default=6)
     ap.add_argument("--n-biter", type=int, default=3)
+    ap.add_argument("--alpha", type=float, default=0.003)
+    ap.add_argument("--max-iter", type=int, default=0, help="cap of the per-level iteration count (default 4 x n-iter)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -31,10 +33,12 @@ def main():
     # measurements of the whole stack, synthesised on the device two slices at a time, parked in pinned host memory
     meas = torch.empty((S,) + P.sino_shape, dtype=torch.float32, pin_memory=True)
     x0 = torch.full((S, 2, n, n), 0.5, dtype=torch.float32).pin_memory()
+    gts = torch.empty((S, 2, n, n), dtype=torch.float32)
     for s in range(0, S, 2):
         gt = torch.from_numpy(np.stack([phantoms.two_discs(n, z=(s + i) / S) for i in range(min(2, S - s))])).cuda()
+        gts[s:s + gt.shape[0]] = gt.cpu()
         meas[s:s + gt.shape[0]] = synthesis.white_sinogram(P, sp, gt.reshape(-1, n, n)).reshape((-1,) + P.sino_shape).cpu()
-    params = dict(n_iter=args.n_iter, n_biter=args.n_biter, alpha=0.003, max_iter=4 * args.n_iter)
+    params = dict(n_iter=args.n_iter, n_biter=args.n_biter, alpha=args.alpha, max_iter=args.max_iter or 4 * args.n_iter)
     solvers.white_barrier_reconstruct(P, sp, meas[:4], x0[:4], batch=4, n_iter=2, n_biter=1, alpha=0.003)   # warm-up
     torch.cuda.synchronize()
     t = time.perf_counter()
@@ -45,12 +49,16 @@ def main():
     its, ni = 0, args.n_iter
     for _ in range(args.n_biter):
         its += ni
-        ni = min(int(ni / 0.5), 4 * args.n_iter)
+        ni = min(int(ni / 0.5), params["max_iter"])
+    mine = gts[s0:s1]
+    err0 = float(torch.linalg.vector_norm(x0[s0:s1] - mine) / torch.linalg.vector_norm(mine))
+    err = float(torch.linalg.vector_norm(out - mine) / torch.linalg.vector_norm(mine))
     rate = (s1 - s0) * its / dt
     print(json.dumps({"rank": rank, "world": world, "slices": [s0, s1], "batch": args.batch, "iterations_per_slice_max": its,
                       "wall_s": dt, "slice_iterations_per_s_lower_bound": rate,
                       "gups_lower_bound": rate * 4 * n * n * na / 1e9,
                       "full_stack_2048_slices_same_schedule_s": 2048 / world * its / rate,
+                      "rel_l2_to_ground_truth_start": err0, "rel_l2_to_ground_truth_end": err,
                       "finite": bool(torch.isfinite(out).all()), "in_box": bool(((out >= 0) & (out <= 1)).all())}), flush=True)
 
 
