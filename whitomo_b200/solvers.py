@@ -213,13 +213,19 @@ def barrier_least_squares(proj, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t
         u, st = fused_fp(t)
         for _ in range(n_iter):
             g = proj.bp(u)
-            proj.barrier_update(x, g, alpha, beta_reg, t, lower_only=True, mode=_capi.UPD_STEP_ONLY)
+            # the step's own barrier penalty -sum(log x') is +inf or nan exactly when some pixel left x > 0: the
+            # reference's `clip to x >= 0` test (src/barrier_method.py:201-206) without a pass over the volume
+            pen = proj.barrier_update(x, g, alpha, beta_reg, t, lower_only=True, mode=_capi.UPD_STEP_ONLY,
+                                      want_penalty=True)
             u, st = fused_fp(t)                     # P at the stepped point: feasibility + next gradient
+            infeasible, left_box = torch.stack([(st[:, 2] > 0).any(),
+                                                ((pen == float("inf")) | torch.isnan(pen)).any()]).tolist()   # one sync
             dirty = False
-            if with_sino_barrier and bool((st[:, 2] > 0).any()):
+            if with_sino_barrier and infeasible:
                 x = _bc_project(proj, x, m_hb, b_hb)
                 dirty = True
-            if bool((x < 0).any()):
+                left_box = bool((x < 0).any())
+            if left_box:
                 proj.barrier_update(x, None, 0.0, beta_reg, 0.0, lower_only=True, mode=_capi.UPD_CLIP_ONLY)
                 dirty = True
             if dirty:
