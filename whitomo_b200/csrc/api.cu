@@ -265,7 +265,7 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     if (padl < 4) padl = 4;
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
-    g->sino_pitch = (padl + ndet + padl + BP_SEGW + 3) & ~3;
+    g->sino_pitch = (padl + ndet + padl + BP_SEGW_MAX + 3) & ~3;
     g->d_fp = nullptr; g->d_bp = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
     g->nphase = nphase;
     for (int i = 0; i <= FP_MAX_PHASES; ++i) g->phase_start[i] = phase_start[i];

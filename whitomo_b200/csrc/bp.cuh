@@ -2,10 +2,10 @@
 //   v[row, col] = sum_a  w0 * q[a, d0] + w1 * q[a, d0 + 1],   d0 = floor(d*),  f = d* - d0,
 //   w0 = max(0, A0 - B f),  w1 = max(0, A1 + B f)           (triangle of half-width m, height 1/m).
 //
-// A CTA owns a BP_TW x BP_TH pixel tile and keeps 8 pixels x V images per thread in registers.  For
-// every block of BP_AB angles a dedicated producer warp computes, per angle, where the tile's shadow falls
-// on the detector and asks the TMA unit (cp.async.bulk, one 1-D bulk copy per angle) to stage that
-// BP_SEGW-wide sinogram segment in shared memory.  A full/empty mbarrier pair per stage, BP_STAGES deep,
+// A CTA owns a BP_TW x TH pixel tile (TH = 32, or 16 for small volumes) and keeps TH/4 pixels x V images per thread in
+// registers.  For every block of BP_AB angles a dedicated producer warp computes, per angle, where the tile's shadow
+// falls on the detector and asks the TMA unit (cp.async.bulk, one 1-D bulk copy per angle) to stage that 80- (72-)
+// detector sinogram segment in shared memory.  A full/empty mbarrier pair per stage, BP_STAGES deep,
 // lets the copies of later angle blocks overlap the gather of the current one and lets the 8 consumer
 // warps run without ever synchronising with each other.
 // Lanes run along image columns: their detector positions differ by |cos| <= 1, so the LDS of a warp
@@ -85,10 +85,10 @@ template <int V> struct BpShare { static constexpr int value = V >= 4 ? WT_BP_NS
 // tile row of a consumer thread's r-th pixel row: vertically adjacent pairs 2*warp + {0, 1}, then 16 rows further down
 __host__ __device__ constexpr int bp_row_of(int warp, int r) { return 2 * warp + 16 * (r >> 1) + (r & 1); }
 
-template <int V>
+template <int V, int TH>
 struct BpSmem {
     typedef typename VecOf<V>::T VecT;
-    VecT seg[BP_STAGES][BP_AB][BP_SEGW];
+    VecT seg[BP_STAGES][BP_AB][BpTile<TH>::SEGW];
     float4 cst[BP_STAGES][BP_AB];  // dcol, drow, base - 1/2, Ah = A0 - B/2
     float2 cst2[BP_STAGES][BP_AB]; // B, unused
     uint64_t full[BP_STAGES];   // TMA bytes of a stage have landed
@@ -97,11 +97,12 @@ struct BpSmem {
 
 // Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
 // MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
-template <int V, class Epi, bool MIRROR>
+template <int V, class Epi, bool MIRROR, int TH>
 __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
+    constexpr int BP_TH = TH, BP_RPT = BpTile<TH>::RPT, BP_SEGW = BpTile<TH>::SEGW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BpSmem<V> &sm = *reinterpret_cast<BpSmem<V> *>(smem_raw);
+    BpSmem<V, TH> &sm = *reinterpret_cast<BpSmem<V, TH> *>(smem_raw);
 
     const int g = blockIdx.z;
     const int col0 = blockIdx.x * BP_TW, row0 = blockIdx.y * BP_TH;
@@ -276,20 +277,35 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
     }
 }
 
-template <int V, class Epi, bool MIRROR = false>
-inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
-    const size_t smem = sizeof(BpSmem<V>);
+// Tile height.  A 64 x 32 tile is the faster one when there are CTAs to spare (23.2 vs 24.1 ms at 2048^2 x 16 images),
+// but a 512^2 volume has only 128 of them for 148 SMs: volumes of at most one 64 x 32 tile per SM use 64 x 16 tiles
+// (measured BP: 256^2 43 -> 30 us, 512^2 78 -> 66 us per image).  The choice depends on the volume alone, never on the
+// number of images, so that an image's bits do not depend on the batch it travels in.
+inline int bp_tile_height(int rows, int cols) {
+    const long tiles32 = (long)((cols + BP_TW - 1) / BP_TW) * ((rows + 31) / 32);
+    return tiles32 <= 148 ? 16 : 32;
+}
+
+template <int V, class Epi, bool MIRROR, int TH>
+inline cudaError_t launch_bp_th(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
+    const size_t smem = sizeof(BpSmem<V, TH>);
     static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi, MIRROR, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.Rproc + BP_TH - 1) / BP_TH, groups);
-    bp_kernel<V, Epi, MIRROR><<<grid, BP_BLOCK, smem, st>>>(p, epi);
+    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.Rproc + TH - 1) / TH, groups);
+    bp_kernel<V, Epi, MIRROR, TH><<<grid, BP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
+}
+
+template <int V, class Epi, bool MIRROR = false>
+inline cudaError_t launch_bp(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
+    if (bp_tile_height(p.R, p.C) == 16) return launch_bp_th<V, Epi, MIRROR, 16>(p, epi, groups, st);
+    return launch_bp_th<V, Epi, MIRROR, 32>(p, epi, groups, st);
 }
 
 }  // namespace wt

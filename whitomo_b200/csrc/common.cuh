@@ -15,22 +15,24 @@ namespace wt {
 // predicates in the projector's inner loop.
 constexpr int VPAD = 4;
 
-// Backprojector tile: BP_TW x BP_TH pixels per CTA, BP_AB angles per TMA stage, BP_STAGES stages.
+// Backprojector tile: BP_TW x TH pixels per CTA (TH = 32, or 16 for small volumes, see bp_tile_height), BP_AB angles per
+// TMA stage, BP_STAGES stages.
 constexpr int BP_TW = 64;
-#ifndef WT_BP_TH
-#define WT_BP_TH 32
-#endif
 #ifndef WT_BP_STAGES
 #define WT_BP_STAGES 3
 #endif
 #ifndef WT_BP_AB
 #define WT_BP_AB 16
 #endif
-constexpr int BP_TH = WT_BP_TH;          // 8 consumer warps x BP_RPT rows
-constexpr int BP_RPT = BP_TH / 8;        // rows per thread
 constexpr int BP_AB = WT_BP_AB;
 constexpr int BP_STAGES = WT_BP_STAGES;
-constexpr int BP_SEGW = BP_TH >= 32 ? 80 : 72;  // staged segment width (>= tile diagonal + 8, multiple of 4)
+// staged segment width per tile height (>= tile diagonal + 8, multiple of 4): 8 consumer warps x TH/8 rows per thread
+template <int TH> struct BpTile {
+    static_assert(TH == 16 || TH == 32, "tile heights: 16 or 32 rows");
+    static constexpr int RPT = TH / 8;                 // rows per thread
+    static constexpr int SEGW = TH >= 32 ? 80 : 72;
+};
+constexpr int BP_SEGW_MAX = 80;
 constexpr int BP_THREADS = 256;            // consumer threads
 constexpr int BP_BLOCK = BP_THREADS + 32;  // + one producer warp that only drives the TMA pipeline
 
