@@ -97,37 +97,50 @@ struct FpEpiWhite {
             __syncthreads();
         }
         const float *tb = in_smem ? scratch : tab;
-        // the bin loop, once per table source so that the constant-memory version compiles to LDC (a pointer chosen at
-        // run time would turn both into generic loads)
-        auto bins = [&](auto table, const float *P, float &I, float (&mu)[K]) {
+        // The bin loop runs once over the tables for all slices of the group (the table reads are shared), and once
+        // per table source so that the constant-memory version compiles to LDC (a pointer chosen at run time would
+        // turn both into generic loads).  Padding slices compute on zeros and are not stored.
+        float I[SPG], mu[SPG][K];
+#pragma unroll
+        for (int sl = 0; sl < SPG; ++sl) {
+            I[sl] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) mu[sl][k] = 0.0f;
+        }
+        auto bins = [&](auto table) {
             for (int e = 0; e < E; ++e) {
                 const float sw = table(e);
-                float ab[K], arg = 0.0f;
+                float ab[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) { ab[k] = table((k + 1) * E + e); arg = fmaf(ab[k], P[k], arg); }
-                const float t = sw * ex2_ftz(-arg);           // tables are pre-scaled by log2(e): one MUFU.EX2
-                I += t;
+                for (int k = 0; k < K; ++k) ab[k] = table((k + 1) * E + e);
 #pragma unroll
-                for (int k = 0; k < K; ++k) mu[k] = fmaf(t, ab[k], mu[k]);
+                for (int sl = 0; sl < SPG; ++sl) {
+                    float arg = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) arg = fmaf(ab[k], val[sl * K + k], arg);
+                    const float t = sw * ex2_ftz(-arg);       // tables are pre-scaled by log2(e): one MUFU.EX2
+                    I[sl] += t;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) mu[sl][k] = fmaf(t, ab[k], mu[sl][k]);
+                }
             }
         };
-        const int cbase = in_const ? cslot * WT_CTAB : 0;
+        if (valid) {
+            const int cbase = in_const ? cslot * WT_CTAB : 0;
+            if (in_const) bins([&](int i) { return c_spectrum_tab[cbase + i]; });
+            else bins([&](int i) { return tb[i]; });
+        }
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
             const bool real = (g * SPG + sl) * K < p.nimg;      // else: padding slice of the last group
             float q2 = 0.0f;
             if (valid && real) {
-                float I = 0.0f, mu[K], P[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) { mu[k] = 0.0f; P[k] = val[sl * K + k]; }
-                if (in_const) bins([&](int i) { return c_spectrum_tab[cbase + i]; }, P, I, mu);
-                else bins([&](int i) { return tb[i]; }, P, I, mu);
-                const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I;
-                if (inten) inten[slice * plane + r] = I;
+                const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I[sl];
+                if (inten) inten[slice * plane + r] = I[sl];
                 if (qmu) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-0.6931471805599453f * mu[k]);
+                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-0.6931471805599453f * mu[sl][k]);
                 }
                 q2 = q * q;
             }
