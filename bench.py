@@ -156,7 +156,8 @@ def run_reference(args):
     threads = oracle.num_threads()
     probe = max(32, 2 * threads)
     dt, _ = cpu_grad_sample(probe, threads)               # probe, also warms the page cache
-    n_s = int(max(probe, min(A, probe * 6.0 / max(dt, 1e-3))))   # ~6 s per step
+    target_s = float(os.environ.get("WT_BENCH_REF_SECONDS", "6"))         # CPU seconds per step (tests shrink it)
+    n_s = int(max(probe, min(A, probe * target_s / max(dt, 1e-3))))
     for _ in range(min(args.warmup, 1)):
         cpu_grad_sample(n_s, threads)
     times, upd = [], 0.0
