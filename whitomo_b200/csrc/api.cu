@@ -79,18 +79,21 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     for (int i = 0; i <= FP_MAX_PHASES; ++i) p.phase_start[i] = g->phase_start[i];
     p.ndblk = 0;   // set by launch_fp from Dproc
     p.nimg = n;
+    // only the packed copies the angles of this call read: an angle-range call of one orientation packs half
+    int copies = 0;
+    for (int a = a_begin; a < a_end; ++a) copies |= g->h_vertical[a] ? 1 : 2;
     const Epi epi = epi_proto;
     if (use_mirror(g, n)) {
         p.Dproc = (g->ndet + 1) / 2;
         if (n == 1) {
             if constexpr (Epi::kMult == 1) {
-                launch_pack_vol<2, true>(vol, vn, vt, p.R, p.C, 1, n, st);
+                launch_pack_vol<2, true>(vol, vn, vt, p.R, p.C, 1, n, copies, st);
                 WT_CUDA((launch_fp<2, Epi, true>(p, epi, 1, st)));
             } else {
                 return invalid("run_fp: image count is not a multiple of the element count");
             }
         } else {
-            launch_pack_vol<4, true>(vol, vn, vt, p.R, p.C, 1, n, st);
+            launch_pack_vol<4, true>(vol, vn, vt, p.R, p.C, 1, n, copies, st);
             WT_CUDA((launch_fp<4, Epi, true>(p, epi, 1, st)));
         }
         WT_CUDA(cudaGetLastError());
@@ -100,12 +103,12 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     if (n % Epi::kMult) return invalid("run_fp: image count is not a multiple of the element count");
     const Chunk c = chunk_of(n);
     switch (c.v) {
-    case 4: launch_pack_vol<4>(vol, vn, vt, p.R, p.C, c.groups, n, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
+    case 4: launch_pack_vol<4>(vol, vn, vt, p.R, p.C, c.groups, n, copies, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
     case 2:
-        if constexpr (2 % Epi::kMult == 0) { launch_pack_vol<2>(vol, vn, vt, p.R, p.C, 1, n, st); WT_CUDA((launch_fp<2, Epi>(p, epi, 1, st))); }
+        if constexpr (2 % Epi::kMult == 0) { launch_pack_vol<2>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<2, Epi>(p, epi, 1, st))); }
         break;
     default:
-        if constexpr (Epi::kMult == 1) { launch_pack_vol<1>(vol, vn, vt, p.R, p.C, 1, n, st); WT_CUDA((launch_fp<1, Epi>(p, epi, 1, st))); }
+        if constexpr (Epi::kMult == 1) { launch_pack_vol<1>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<1, Epi>(p, epi, 1, st))); }
         break;
     }
     WT_CUDA(cudaGetLastError());
@@ -124,17 +127,17 @@ static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a
     const Epi epi = epi_proto;
     if (use_mirror(g, n)) {
         p.Rproc = (g->rows + 1) / 2;
-        if (n == 1) { launch_pack_sino<2, true>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
-        else { launch_pack_sino<4, true>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
+        if (n == 1) { launch_pack_sino<2, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
+        else { launch_pack_sino<4, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
         WT_CUDA(cudaGetLastError());
         return WT_OK;
     }
     p.Rproc = g->rows;
     const Chunk c = chunk_of(n);
     switch (c.v) {
-    case 4: launch_pack_sino<4>(sino, sp, g, c.groups, n, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
-    case 2: launch_pack_sino<2>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
-    default: launch_pack_sino<1>(sino, sp, g, 1, n, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
+    case 4: launch_pack_sino<4>(sino, sp, g, c.groups, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
+    case 2: launch_pack_sino<2>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
+    default: launch_pack_sino<1>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
     }
     WT_CUDA(cudaGetLastError());
     return WT_OK;
@@ -272,6 +275,8 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     g->ntiles = (int)tiles.size();
     g->h_angles = (float *)malloc(sizeof(float) * nangles);
     memcpy(g->h_angles, angles, sizeof(float) * nangles);
+    g->h_vertical = (unsigned char *)malloc(nangles);
+    for (int a = 0; a < nangles; ++a) g->h_vertical[a] = (unsigned char)fp[a].vertical;
     cudaError_t e = cudaMalloc(&g->d_fp, sizeof(FpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_bp, sizeof(BpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_fp, fp.data(), sizeof(FpAngle) * nangles, cudaMemcpyHostToDevice);
@@ -295,6 +300,7 @@ void wt_geom_destroy(wt_geom *g) {
     if (g->d_tiles) cudaFree(g->d_tiles);
     if (g->d_order) cudaFree(g->d_order);
     free(g->h_angles);
+    free(g->h_vertical);
     delete g;
 }
 

@@ -22,11 +22,11 @@ namespace wt {
 // (pixel (R-1-row, C-1-col) sees detector coordinate (D-1) - d*, see the kernel's epilogue)
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict__ sino, float *__restrict__ sp, int A,
-                                                        int D, int padl, int pitch, int nimg) {
+                                                        int D, int padl, int pitch, int nimg, int a_begin) {
     static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
     constexpr int V0 = MIRROR ? V / 2 : V;
-    const int g = blockIdx.z, a = blockIdx.y;
+    const int g = blockIdx.z, a = a_begin + blockIdx.y;      // only the angles the backprojection will read
     const size_t plane = (size_t)A * D;
     for (int dp = blockIdx.x * blockDim.x + threadIdx.x; dp < pitch; dp += gridDim.x * blockDim.x) {
         const int d = dp - padl;
@@ -42,9 +42,11 @@ __global__ void __launch_bounds__(256) pack_sino_kernel(const float *__restrict_
 }
 
 template <int V, bool MIRROR = false>
-inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, int nimg, cudaStream_t st) {
-    dim3 grid((g->sino_pitch + 255) / 256, g->nangles, groups);
-    pack_sino_kernel<V, MIRROR><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch, nimg);
+inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int groups, int nimg, int a_begin, int a_end,
+                             cudaStream_t st) {
+    if (a_end <= a_begin) return;
+    dim3 grid((g->sino_pitch + 255) / 256, a_end - a_begin, groups);
+    pack_sino_kernel<V, MIRROR><<<grid, 256, 0, st>>>(sino, sp, g->nangles, g->ndet, g->sino_padl, g->sino_pitch, nimg, a_begin);
 }
 
 struct BpParams {

@@ -76,6 +76,7 @@ struct wt_geom {
     int nphase;
     int phase_start[5];
     float *h_angles;
+    unsigned char *h_vertical;   // per angle: 1 if the projector marches over rows (reads VN), 0 if over columns (VT)
 };
 
 struct wt_spectrum {

@@ -52,7 +52,7 @@ __host__ __device__ inline int fp_pitch(int npos) {
 // run through the V = 2 / V = 4 kernels with half the rays and shared index arithmetic (DESIGN.md "mirror pairing").
 template <int V, bool MIRROR = false>
 __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__ vol, float *__restrict__ vn,
-                                                       float *__restrict__ vt, int R, int C, int nimg) {
+                                                       float *__restrict__ vt, int R, int C, int nimg, int copies) {
     static_assert(!MIRROR || V % 2 == 0, "mirror pairing needs an even interleave width");
     typedef typename VecOf<V>::T VecT;
     constexpr int V0 = MIRROR ? V / 2 : V;   // images per group
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
             else v[i] = in && real ? __ldg(src + i * img + (size_t)r * C + c) : 0.0f;
             tile[i][rr][tx] = v[i];
         }
-        if (r >= 0 && r < R && c + VPAD < Cp)
+        if ((copies & 1) && r >= 0 && r < R && c + VPAD < Cp)
             reinterpret_cast<VecT *>(vn)[((size_t)g * R + r) * Cp + (c + VPAD)] = pack<V>(v);
     }
+    if (!(copies & 2)) return;      // uniform over the grid: no transposed copy wanted
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -94,12 +95,13 @@ __global__ void __launch_bounds__(256) pack_vol_kernel(const float *__restrict__
     }
 }
 
+// copies: bit 0 = row-major copy VN (read by vertical angles), bit 1 = transposed copy VT (horizontal angles)
 template <int V, bool MIRROR = false>
-inline void launch_pack_vol(const float *vol, float *vn, float *vt, int R, int C, int groups, int nimg, cudaStream_t st) {
+inline void launch_pack_vol(const float *vol, float *vn, float *vt, int R, int C, int groups, int nimg, int copies, cudaStream_t st) {
     // the tile grid covers the padded extents of both copies (pitch may exceed npos + 2*VPAD for tiny volumes)
     const int ext_c = max(fp_pitch(C), C + 2 * VPAD), ext_r = max(fp_pitch(R), R + 2 * VPAD);
     dim3 grid((ext_c + 31) / 32, (ext_r + 31) / 32, groups);
-    pack_vol_kernel<V, MIRROR><<<grid, dim3(32, 8), 0, st>>>(vol, vn, vt, R, C, nimg);
+    pack_vol_kernel<V, MIRROR><<<grid, dim3(32, 8), 0, st>>>(vol, vn, vt, R, C, nimg, copies);
 }
 
 // ---- projector ------------------------------------------------------------------------------------
