@@ -37,6 +37,11 @@ typedef struct wt_spectrum wt_spectrum; /* polychromatic source / absorption tab
 
 const char *wt_last_error(void);
 int wt_version(void);
+/* Diagnostic (no counterpart in the reference): shared-memory gather indices of K1/K2 found outside their staged
+ * window since the library was loaded.  Always 0 unless the library was built with -DWT_BOUNDS_CHECK=1 (the checks
+ * cost ~10 % and are compiled out of the product build); the GPU test suite is run once against such a build in place
+ * of compute-sanitizer, which is not available on the measurement pool.  Synchronises the device. */
+long long wt_debug_oob_count(void);
 
 /* Replaces astra.create_proj_geom('parallel', det_width, ndet, angles) + astra.create_vol_geom(rows, cols)
  * + astra.create_projector('linear', pg, vg)  (src/white_projection.py:41-63, src/white_rec.py:66-74,

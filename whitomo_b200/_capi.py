@@ -13,6 +13,7 @@ c_int, c_float, c_double, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, cty
 SIGNATURES = {
     "wt_last_error": (ctypes.c_char_p, []),
     "wt_version": (c_int, []),
+    "wt_debug_oob_count": (ctypes.c_longlong, []),
     "wt_geom_create": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_void_p)]),
     "wt_geom_destroy": (None, [c_void_p]),
     "wt_geom_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),

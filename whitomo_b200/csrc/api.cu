@@ -164,6 +164,13 @@ extern "C" {
 const char *wt_last_error(void) { return g_err.c_str(); }
 int wt_version(void) { return 100; }
 
+long long wt_debug_oob_count(void) {
+    unsigned long long n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, g_oob_count, sizeof(n)) != cudaSuccess) return -1;
+    return (long long)n;
+}
+
 int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, wt_geom **out) {
     if (!out || !angles) return invalid("wt_geom_create: null pointer");
     if (rows <= 0 || cols <= 0 || ndet <= 0 || nangles <= 0) return invalid("wt_geom_create: sizes must be positive");

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         int idx;
         float f;
         locate(ds, idx, f);
+        check_index(idx, idx + 1, BP_SEGW);
         const float w0 = fmaxf(0.0f, fmaf(-bw, f, c4.w)), w1 = fmaxf(0.0f, fmaf(bw, f, c4.w));
         float v0[V], v1[V];
         unpack<V>(seg[idx], v0);
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         int idx;
         float f0;
         locate(ds, idx, f0);
+        check_index(POS ? idx : idx - 1, POS ? idx + 2 : idx + 1, BP_SEGW);
         const float g = f0 + c4.y;
         const bool moved = POS ? (g >= 0.5f) : (g < -0.5f);
         const float f1 = moved ? (POS ? g - 1.0f : g + 1.0f) : g;

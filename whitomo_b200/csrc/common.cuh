@@ -153,6 +153,17 @@ __device__ __forceinline__ void tap_triple_fma(float w0, const float (&v0)[V], f
     }
 }
 
+// ---- optional bounds checks of the shared-memory gathers (-DWT_BOUNDS_CHECK=1, see wt_debug_oob_count) -------------
+#ifndef WT_BOUNDS_CHECK
+#define WT_BOUNDS_CHECK 0
+#endif
+__device__ unsigned long long g_oob_count;
+__device__ __forceinline__ void check_index(int lo, int hi, int limit) {   // the gather reads slots [lo, hi] of [0, limit)
+#if WT_BOUNDS_CHECK
+    if (lo < 0 || hi >= limit) atomicAdd(&g_oob_count, 1ull);
+#endif
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
                     const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
                     const float off = (cr - (t - MAGIC)) + 0.5f;
                     const int idx = __float_as_int(t) - MAGIC_BITS;
+                    check_index(idx, idx + 1, FP_W);
                     float v0[V], v1[V];
                     unpack<V>(row[idx], v0);
                     unpack<V>(row[idx + 1], v1);
