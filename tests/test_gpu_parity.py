@@ -329,3 +329,19 @@ def test_wide_detector_pixels_and_unordered_angles(eng, det_width):
         assert rel_l2(p[i], oracle.fp(g, x[i])) < TOL_OP
         assert rel_l2(v[i], oracle.bp(g, y[i])) < TOL_OP
     assert np.array_equal(p[:, 4], p[:, 5])                # the repeated view
+
+
+def test_repeated_calls_are_bit_identical(eng):
+    """the TMA / mbarrier pipelines hand stages between a producer warp and 8 consumer warps with no other
+    synchronisation; a hand-off race would show up as run-to-run differences"""
+    Projector, _ = eng
+    n, a = 384, 300
+    d = int(np.sqrt(2) * n + 1)
+    P = Projector(n, n, d, np.linspace(0, np.pi, a))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for nimg in (1, 2, 6):
+        x = torch.rand(nimg, n, n, device="cuda", generator=g)
+        y = torch.rand(nimg, a, d, device="cuda", generator=g)
+        p0, v0 = P.fp(x).clone(), P.bp(y).clone()
+        for _ in range(10):
+            assert torch.equal(P.fp(x), p0) and torch.equal(P.bp(y), v0)
