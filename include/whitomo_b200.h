@@ -43,6 +43,14 @@ int wt_version(void);
  * of compute-sanitizer, which is not available on the measurement pool.  Synchronises the device. */
 long long wt_debug_oob_count(void);
 
+/* Diagnostic, host only (no CUDA call): what wt_geom_create plans for a geometry -- the forward projector's angle
+ * tiles (consecutive angles of one orientation that share a staging window; first angle, angle count, orientation) and
+ * the order the tiles are launched in (phase by phase; phase_start holds 5 prefix offsets into launch_order).  Arrays
+ * may be null; at most max_tiles entries are written, *n_tiles receives the tile count. */
+int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, int max_tiles,
+                 int *tile_first, int *tile_count, int *tile_vertical, int *launch_order, int *n_tiles, int *n_phases,
+                 int *phase_start);
+
 /* Replaces astra.create_proj_geom('parallel', det_width, ndet, angles) + astra.create_vol_geom(rows, cols)
  * + astra.create_projector('linear', pg, vg)  (src/white_projection.py:41-63, src/white_rec.py:66-74,
  * teeth_recon/experiments.py:228-235).  `angles` is a HOST array (radians, cast to float32 like ASTRA). */

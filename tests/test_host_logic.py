@@ -171,3 +171,86 @@ def test_synthetic_inputs():
     assert c.shape == (2, 256, 256) and abs(c[0].sum() - 7845) < 60 and abs(c[1].sum() - 1257) < 30
     t = phantoms.tooth_phantom(64)
     assert np.allclose(np.unique(t), [0, phantoms.CA_LEVEL, phantoms.AU_LEVEL])
+
+
+def _plan(rows, cols, ndet, angles, det_width=1.0):
+    from whitomo_b200 import _capi
+    lib = _capi.load()
+    ang = np.ascontiguousarray(np.asarray(angles, dtype=np.float64).astype(np.float32))
+    cap = len(ang)
+    ip = ctypes.POINTER(ctypes.c_int)
+    first, count, vert, order = (np.zeros(cap, np.int32) for _ in range(4))
+    nt, nph = ctypes.c_int(), ctypes.c_int()
+    ps = np.zeros(5, np.int32)
+    rc = lib.wt_geom_plan(rows, cols, ndet, det_width, ang.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), len(ang), cap,
+                          first.ctypes.data_as(ip), count.ctypes.data_as(ip), vert.ctypes.data_as(ip),
+                          order.ctypes.data_as(ip), ctypes.byref(nt), ctypes.byref(nph), ps.ctypes.data_as(ip))
+    assert rc == 0, lib.wt_last_error()
+    n = nt.value
+    return first[:n], count[:n], vert[:n], order[:n], nph.value, ps
+
+
+@pytest.mark.parametrize("n,na", [(10, 35), (256, 180), (1024, 720), (2048, 1800), (8192, 4096), (4096, 300)])
+def test_forward_projector_plan_invariants(n, na):
+    """host-side planning of K1 (no CUDA involved): the angle tiles partition the angle list in order, hold at most 8
+    angles of one orientation whose rays stay within the staged window, and the launch order is a permutation of the
+    tiles grouped by orientation"""
+    ang = np.linspace(0, np.pi, na)
+    d = int(np.sqrt(2) * n + 1)
+    first, count, vert, order, nph, ps = _plan(n, n, d, ang)
+    assert first[0] == 0 and np.array_equal(first[1:], (first + count)[:-1]) and first[-1] + count[-1] == na
+    assert count.min() >= 1 and count.max() <= 8
+    a32 = ang.astype(np.float32).astype(np.float64)
+    vertical = np.abs(np.float32(np.sin(a32))) < np.abs(np.float32(np.cos(a32)))          # |ray_x| < |ray_y| on float32 values
+    for f, c, v in zip(first, count, vert):
+        assert (vertical[f:f + c] == bool(v)).all()
+    # adequately sampled geometries (A >= N) keep their tiles (almost) full; under-sampled ones fall back to small tiles
+    if na >= n and na >= 180:
+        assert count.mean() >= 6.0
+    if na * 8 < n:
+        assert count.mean() < 6.0
+    # launch order: permutation, one phase per orientation, phases contiguous
+    assert sorted(order.tolist()) == list(range(len(first)))
+    assert nph in (1, 2) and ps[0] == 0 and ps[nph] == len(first)
+    for ph in range(nph):
+        tiles = order[ps[ph]:ps[ph + 1]]
+        assert len(set(vert[tiles].tolist())) == 1
+        assert np.array_equal(tiles, np.sort(tiles))             # angle order inside a phase
+
+
+def test_plan_rejects_bad_geometries_without_cuda():
+    from whitomo_b200 import _capi
+    lib = _capi.load()
+    ang = np.zeros(4, np.float32)
+    fp = ang.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    nt = ctypes.c_int()
+    none = ctypes.POINTER(ctypes.c_int)()
+    assert lib.wt_geom_plan(0, 8, 8, 1.0, fp, 4, 0, none, none, none, none, ctypes.byref(nt), none, none) == -1
+    assert lib.wt_geom_plan(8, 8, 8, 0.5, fp, 4, 0, none, none, none, none, ctypes.byref(nt), none, none) == -2
+    assert b"det_width" in lib.wt_last_error()
+    assert lib.wt_geom_plan(8, 8, 8, 1.0, fp, 4, 0, none, none, none, none, ctypes.byref(nt), none, none) == 0 and nt.value >= 1
+
+
+@pytest.mark.parametrize("n,na,ndblk", [(64, 48, 3), (256, 180, 12), (2048, 1800, 91)])
+def test_launch_order_visits_every_cta_once(n, na, ndblk):
+    """fp.cuh: fp_block maps the linear block index to (tile, detector block): phase by phase, detector blocks slowest
+    inside a phase.  Restated here on the planned order: the map must be a bijection onto tiles x detector blocks and
+    keep all tiles of a detector block adjacent (that adjacency is what keeps the lines in flight L2-resident)."""
+    first, count, vert, order, nph, ps = _plan(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
+    ntiles = len(first)
+
+    def fp_block(lin0):
+        s0, s1 = 0, ps[1]
+        for ph in range(1, 4):
+            if ph < nph and lin0 >= ps[ph] * ndblk:
+                s0, s1 = ps[ph], ps[ph + 1]
+        lin, nt = lin0 - s0 * ndblk, s1 - s0
+        dblk = lin // nt
+        return int(order[s0 + lin - dblk * nt]), int(dblk)
+
+    seen = [fp_block(i) for i in range(ntiles * ndblk)]
+    assert len(set(seen)) == ntiles * ndblk
+    assert all(0 <= t < ntiles and 0 <= b < ndblk for t, b in seen)
+    # consecutive CTAs share the detector block except at block / phase boundaries
+    changes = sum(1 for (t0, b0), (t1, b1) in zip(seen, seen[1:]) if b0 != b1)
+    assert changes == nph * ndblk - 1

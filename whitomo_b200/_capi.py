@@ -14,6 +14,7 @@ SIGNATURES = {
     "wt_last_error": (ctypes.c_char_p, []),
     "wt_version": (c_int, []),
     "wt_debug_oob_count": (ctypes.c_longlong, []),
+    "wt_geom_plan": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, c_int] + [ctypes.POINTER(c_int)] * 7),
     "wt_geom_create": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_void_p)]),
     "wt_geom_destroy": (None, [c_void_p]),
     "wt_geom_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),

@@ -155,31 +155,32 @@ typedef BpEpiSirtUpdate HBpSirt;
 static std::mutex g_slot_mutex;
 static unsigned g_slots_used[64] = {};   // bit i of entry d: slot i is taken on device d
 
-}  // namespace wt
+// Everything wt_geom_create derives from the geometry on the host, without touching CUDA: per-angle constants of both
+// projectors, the forward projector's angle tiles and their launch order.  wt_geom_plan exposes it for CPU tests.
+struct GeomPlan {
+    std::vector<FpAngle> fp;
+    std::vector<BpAngle> bp;
+    std::vector<FpTile> tiles;
+    std::vector<int> order;
+    int phase_start[FP_MAX_PHASES + 1];
+    int nphase;
+};
 
-using namespace wt;
-
-extern "C" {
-
-const char *wt_last_error(void) { return g_err.c_str(); }
-int wt_version(void) { return 100; }
-
-long long wt_debug_oob_count(void) {
-    unsigned long long n = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(&n, g_oob_count, sizeof(n)) != cudaSuccess) return -1;
-    return (long long)n;
-}
-
-int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, wt_geom **out) {
-    if (!out || !angles) return invalid("wt_geom_create: null pointer");
-    if (rows <= 0 || cols <= 0 || ndet <= 0 || nangles <= 0) return invalid("wt_geom_create: sizes must be positive");
+static int check_geometry(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, const char *who) {
+    if (!angles) { g_err = std::string(who) + ": null pointer"; return WT_ERR_INVALID; }
+    if (rows <= 0 || cols <= 0 || ndet <= 0 || nangles <= 0) { g_err = std::string(who) + ": sizes must be positive"; return WT_ERR_INVALID; }
     if (!(det_width >= 1.0f)) {
-        g_err = "wt_geom_create: det_width < 1 needs more than two backprojection taps (unsupported)";
+        g_err = std::string(who) + ": det_width < 1 needs more than two backprojection taps (unsupported)";
         return WT_ERR_UNSUPPORTED;
     }
-    std::vector<FpAngle> fp(nangles);
-    std::vector<BpAngle> bp(nangles);
+    return WT_OK;
+}
+
+static void plan_geometry(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, GeomPlan &pl) {
+    pl.fp.assign(nangles, FpAngle());
+    pl.bp.assign(nangles, BpAngle());
+    std::vector<FpAngle> &fp = pl.fp;
+    std::vector<BpAngle> &bp = pl.bp;
     const double Ex = -0.5 * cols + 0.5, Ey = 0.5 * rows - 0.5;
     for (int a = 0; a < nangles; ++a) {
         // the float32 fields ASTRA's vector geometry would hold for this angle
@@ -223,7 +224,8 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     // angle tiles of the forward projector: consecutive angles of one orientation whose rays, over any
     // FP_DT-detector x FP_LB-line patch, stay within FP_WFIT positions of each other.  c_a - c_b is affine in
     // (d, l), so the spread across angles is convex and peaks at a corner of the (d, l) rectangle.
-    std::vector<FpTile> tiles;
+    std::vector<FpTile> &tiles = pl.tiles;
+    tiles.clear();
     {
         auto c_at = [&](int a, int d, int l) { return fp[a].c0_base + ((double)d + 0.5) * fp[a].c0_step + (double)l * fp[a].delta; };
         int a = 0;
@@ -250,8 +252,12 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     }
     // launch order: one phase per orientation (fp.cuh: fp_block); WT_FP_PHASES = 1 | 2 | 4 for experiments
     // (1: all tiles in one phase, 4: orientation x slope sign)
-    std::vector<int> order;
-    int phase_start[FP_MAX_PHASES + 1] = {0, 0, 0, 0, 0}, nphase = 0;
+    std::vector<int> &order = pl.order;
+    order.clear();
+    int (&phase_start)[FP_MAX_PHASES + 1] = pl.phase_start;
+    for (int i = 0; i <= FP_MAX_PHASES; ++i) phase_start[i] = 0;
+    int &nphase = pl.nphase;
+    nphase = 0;
     {
         const char *e = getenv("WT_FP_PHASES");
         int want = e ? atoi(e) : 2;
@@ -267,6 +273,35 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
         }
         for (int i = nphase + 1; i <= FP_MAX_PHASES; ++i) phase_start[i] = phase_start[nphase];
     }
+}
+
+}  // namespace wt
+
+using namespace wt;
+
+extern "C" {
+
+const char *wt_last_error(void) { return g_err.c_str(); }
+int wt_version(void) { return 100; }
+
+long long wt_debug_oob_count(void) {
+    unsigned long long n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, g_oob_count, sizeof(n)) != cudaSuccess) return -1;
+    return (long long)n;
+}
+
+int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, wt_geom **out) {
+    if (!out) return invalid("wt_geom_create: null pointer");
+    if (int rc = check_geometry(rows, cols, ndet, det_width, angles, nangles, "wt_geom_create")) return rc;
+    GeomPlan pl;
+    plan_geometry(rows, cols, ndet, det_width, angles, nangles, pl);
+    const std::vector<FpAngle> &fp = pl.fp;
+    const std::vector<BpAngle> &bp = pl.bp;
+    const std::vector<FpTile> &tiles = pl.tiles;
+    const std::vector<int> &order = pl.order;
+    const int nphase = pl.nphase;
+    const int (&phase_start)[FP_MAX_PHASES + 1] = pl.phase_start;
     wt_geom *g = new wt_geom();
     g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
     // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row
@@ -317,6 +352,26 @@ int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles
     if (cols) *cols = g->cols;
     if (ndet) *ndet = g->ndet;
     if (nangles) *nangles = g->nangles;
+    return WT_OK;
+}
+
+int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, int max_tiles,
+                 int *tile_first, int *tile_count, int *tile_vertical, int *launch_order, int *n_tiles, int *n_phases,
+                 int *phase_start) {
+    if (!n_tiles) return invalid("wt_geom_plan: null pointer");
+    if (int rc = check_geometry(rows, cols, ndet, det_width, angles, nangles, "wt_geom_plan")) return rc;
+    GeomPlan pl;
+    plan_geometry(rows, cols, ndet, det_width, angles, nangles, pl);
+    const int nt = (int)pl.tiles.size();
+    *n_tiles = nt;
+    if (n_phases) *n_phases = pl.nphase;
+    if (phase_start) for (int i = 0; i <= FP_MAX_PHASES; ++i) phase_start[i] = pl.phase_start[i];
+    for (int t = 0; t < nt && t < max_tiles; ++t) {
+        if (tile_first) tile_first[t] = pl.tiles[t].first;
+        if (tile_count) tile_count[t] = pl.tiles[t].count;
+        if (tile_vertical) tile_vertical[t] = pl.fp[pl.tiles[t].first].vertical;
+        if (launch_order) launch_order[t] = pl.order[t];
+    }
     return WT_OK;
 }
 
