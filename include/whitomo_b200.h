@@ -56,6 +56,19 @@ int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *ang
  * teeth_recon/experiments.py:228-235).  `angles` is a HOST array (radians, cast to float32 like ASTRA). */
 int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles,
                    wt_geom **out);
+/* Position arithmetic of both projectors.
+ *   WT_POS_ASTRA (default): the reference's.  ASTRA's 'linear' projector carries a ray's position as a float32 running
+ *     sum, c += delta once per line (the projector behind src/astra_proxy.py:35-66), which drifts away from
+ *     c_0 + l * delta by up to N * ulp(N) / 2 positions (0.1 pixel at 2048^2, 2.5 at 8192^2).  K1 repeats that sum
+ *     literally; K2 inverts its closed form.  This is the mode that matches the reference to 1e-4 at every size.
+ *   WT_POS_EXACT: c_0 + l * delta evaluated in closed form (closer to the continuous operator, 1e-4 .. 1e-2 away from
+ *     the reference at N >= 1024); enables the mirror-paired single-image kernels (1.7x faster for 1-2 images).
+ * wt_geom_create uses WT_POS_ASTRA unless the environment variable WT_POSITIONS is "exact". */
+#define WT_POS_ASTRA 0
+#define WT_POS_EXACT 1
+int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, int positions,
+                      wt_geom **out);
+int wt_geom_positions(const wt_geom *g);
 void wt_geom_destroy(wt_geom *g);
 int wt_geom_dims(const wt_geom *g, int *rows, int *cols, int *ndet, int *nangles);
 

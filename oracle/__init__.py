@@ -53,6 +53,9 @@ def lib():
         for name in ("orc_fp_f64", "orc_bp_f64"):
             getattr(L, name).argtypes = geom + [f64p, f64p]
             getattr(L, name).restype = ctypes.c_int
+        for name in ("orc_fp_f64_mt", "orc_bp_f64_mt"):
+            getattr(L, name).argtypes = geom + [f64p, f64p, ctypes.c_int]
+            getattr(L, name).restype = ctypes.c_int
         L.orc_sirt.argtypes = geom + [f32p, f32p, ctypes.c_int]
         L.orc_sirt.restype = ctypes.c_int
         L.orc_ramp_filter.argtypes = [ctypes.c_int, ctypes.c_int, f32p, f32p]
@@ -125,17 +128,25 @@ def bp(g, sino, threads=1):
     return out
 
 
-def fp64(g, vol):
+def fp64(g, vol, threads=1):
+    """float64 closed-form arbiter of W x (no running sums); threads=0: all host cores, same result"""
     v = np.ascontiguousarray(vol, dtype=np.float64).reshape(g.vol_shape)
     out = np.empty(g.sino_shape, dtype=np.float64)
-    assert lib().orc_fp_f64(*g._args(), _p64(v), _p64(out)) == 0
+    if threads == 1:
+        assert lib().orc_fp_f64(*g._args(), _p64(v), _p64(out)) == 0
+    else:
+        assert lib().orc_fp_f64_mt(*g._args(), _p64(v), _p64(out), int(threads)) == 0
     return out
 
 
-def bp64(g, sino):
+def bp64(g, sino, threads=1):
+    """float64 closed-form arbiter of W^T q (pixel-driven gather form); threads=0: all host cores, same result"""
     s = np.ascontiguousarray(sino, dtype=np.float64).reshape(g.sino_shape)
     out = np.empty(g.vol_shape, dtype=np.float64)
-    assert lib().orc_bp_f64(*g._args(), _p64(s), _p64(out)) == 0
+    if threads == 1:
+        assert lib().orc_bp_f64(*g._args(), _p64(s), _p64(out)) == 0
+    else:
+        assert lib().orc_bp_f64_mt(*g._args(), _p64(s), _p64(out), int(threads)) == 0
     return out
 
 

@@ -252,11 +252,11 @@ int orc_bp_mt(int rows, int cols, int ndet, float detw, const float *angles, int
 
 /* ---- float64 closed-form arbiter (SURVEY A.2 / A.3 formulas, no running sums) ---- */
 
-int orc_fp_f64(int rows, int cols, int ndet, float detw, const float *angles, int nang,
-               const double *vol, double *sino)
+static void fp_f64_range(int rows, int cols, int ndet, float detw, const float *angles, int a0, int a1,
+                         const double *vol, double *sino)
 {
     const int R = rows, C = cols, D = ndet;
-    for (int a = 0; a < nang; ++a) {
+    for (int a = a0; a < a1; ++a) {
         float thf = angles[a];
         double th = (double)thf;
         double cs = cos(th), sn = sin(th);
@@ -293,22 +293,28 @@ int orc_fp_f64(int rows, int cols, int ndet, float detw, const float *angles, in
             sino[(size_t)a * D + d] = acc;
         }
     }
+}
+
+int orc_fp_f64(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+               const double *vol, double *sino)
+{
+    fp_f64_range(rows, cols, ndet, detw, angles, 0, nang, vol, sino);
     return 0;
 }
 
 /* pixel-driven gather form of the exact transpose, float64 */
-int orc_bp_f64(int rows, int cols, int ndet, float detw, const float *angles, int nang,
-               const double *sino, double *vol)
+static void bp_f64_rows(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+                        const double *sino, double *vol, int r0, int r1)
 {
     const int R = rows, C = cols, D = ndet;
-    memset(vol, 0, sizeof(double) * (size_t)R * C);
+    memset(vol + (size_t)r0 * C, 0, sizeof(double) * (size_t)(r1 - r0) * C);
     for (int a = 0; a < nang; ++a) {
         double th = (double)angles[a];
         double cs = cos(th), sn = sin(th);
         int vertical = fabsf((float)(-sn)) < fabsf((float)cs);
         double m = vertical ? fabs(cs) : fabs(sn);
         const double *q = sino + (size_t)a * D;
-        for (int row = 0; row < R; ++row) {
+        for (int row = r0; row < r1; ++row) {
             double y = 0.5 * R - 0.5 - row;
             for (int col = 0; col < C; ++col) {
                 double x = col - 0.5 * C + 0.5;
@@ -331,7 +337,62 @@ int orc_bp_f64(int rows, int cols, int ndet, float detw, const float *angles, in
             }
         }
     }
+}
+
+int orc_bp_f64(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+               const double *sino, double *vol)
+{
+    bp_f64_rows(rows, cols, ndet, detw, angles, nang, sino, vol, 0, rows);
     return 0;
+}
+
+/* all-host-cores variants of the float64 arbiter: FP over angle ranges, BP over row ranges (same arithmetic and
+ * summation order per output element as the single-thread functions) */
+typedef struct {
+    int rows, cols, ndet, nang, lo, hi, is_bp;
+    float detw;
+    const float *angles;
+    const double *in;
+    double *out;
+} f64_job;
+
+static void *f64_run(void *arg)
+{
+    f64_job *j = (f64_job *)arg;
+    if (j->is_bp) bp_f64_rows(j->rows, j->cols, j->ndet, j->detw, j->angles, j->nang, j->in, j->out, j->lo, j->hi);
+    else fp_f64_range(j->rows, j->cols, j->ndet, j->detw, j->angles, j->lo, j->hi, j->in, j->out);
+    return NULL;
+}
+
+static int f64_mt(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+                  const double *in, double *out, int nthreads, int is_bp)
+{
+    int nth = mt_threads(nthreads);
+    const int total = is_bp ? rows : nang;
+    if (nth > total) nth = total;
+    pthread_t th[256];
+    f64_job jobs[256];
+    for (int t = 0; t < nth; ++t) {
+        f64_job *j = &jobs[t];
+        j->rows = rows; j->cols = cols; j->ndet = ndet; j->nang = nang; j->detw = detw; j->angles = angles;
+        j->in = in; j->out = out; j->is_bp = is_bp;
+        j->lo = (int)((long)total * t / nth); j->hi = (int)((long)total * (t + 1) / nth);
+        if (pthread_create(&th[t], NULL, f64_run, j)) return -2;
+    }
+    for (int t = 0; t < nth; ++t) pthread_join(th[t], NULL);
+    return 0;
+}
+
+int orc_fp_f64_mt(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+                  const double *vol, double *sino, int nthreads)
+{
+    return f64_mt(rows, cols, ndet, detw, angles, nang, vol, sino, nthreads, 0);
+}
+
+int orc_bp_f64_mt(int rows, int cols, int ndet, float detw, const float *angles, int nang,
+                  const double *sino, double *vol, int nthreads)
+{
+    return f64_mt(rows, cols, ndet, detw, angles, nang, sino, vol, nthreads, 1);
 }
 
 /* ---- SIRT (ASTRA CSirtAlgorithm, lambda = 1, no constraints). UNPINNED. ---- */

@@ -16,7 +16,7 @@ def P():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from whitomo_b200.projector import Projector
-    return Projector(N, N, int(np.sqrt(2) * N + 1), np.linspace(0, np.pi, NA))
+    return Projector(N, N, int(np.sqrt(2) * N + 1), np.linspace(0, np.pi, NA), positions="exact")
 
 
 def _imgs(n, seed):
@@ -38,7 +38,7 @@ def test_plain_fp_bp(P):
         assert rel_l2(P.bp(y[:n], scale=-2.0)[n - 1].cpu().numpy(), -2.0 * fullb[n - 1].cpu().numpy()) < 1e-5
     # odd row count: the middle row is its own mirror row
     from whitomo_b200.projector import Projector
-    Q = Projector(801, 799, 1133, np.linspace(0, np.pi, 16))
+    Q = Projector(801, 799, 1133, np.linspace(0, np.pi, 16), positions="exact")
     yq = torch.rand((3,) + Q.sino_shape, device="cuda")
     xq = torch.rand((3, 801, 799), device="cuda")
     assert rel_l2(Q.bp(yq[:1])[0].cpu().numpy(), Q.bp(yq)[0].cpu().numpy()) < 1e-5

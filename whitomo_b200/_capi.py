@@ -16,6 +16,8 @@ SIGNATURES = {
     "wt_debug_oob_count": (ctypes.c_longlong, []),
     "wt_geom_plan": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, c_int] + [ctypes.POINTER(c_int)] * 7),
     "wt_geom_create": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_void_p)]),
+    "wt_geom_create_ex": (c_int, [c_int, c_int, c_int, c_float, ctypes.POINTER(c_float), c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "wt_geom_positions": (c_int, [c_void_p]),
     "wt_geom_destroy": (None, [c_void_p]),
     "wt_geom_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "wt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
@@ -43,6 +45,7 @@ class UpdateParams(ctypes.Structure):
 
 
 UPD_STEP_CLIP, UPD_STEP_ONLY, UPD_CLIP_ONLY = 0, 1, 2
+POS_ASTRA, POS_EXACT = 0, 1
 
 _lib = None
 

@@ -61,7 +61,11 @@ static Chunk chunk_of(int n) {
 // Calls with one or two images of a large volume use mirror pairing instead (each image also travels as its point reflection: V = 2n components, half the rays).
 // Pairing halves the number of CTAs, so it only pays once the backprojector still fills the GPU with half its pixel
 // tiles: images of at least 768^2 pixels (measured: 1.3-1.7x faster at 1024^2 and up, slower at 512^2 and below).
-static inline bool use_mirror(const wt_geom *g, int n) { return n <= 2 && (size_t)g->rows * g->cols >= (size_t)768 * 768; }
+// Pairing relies on the symmetry of the exact positions c_0 + l * delta; the reference's float32 running sums are not
+// symmetric (a ray and its mirror image move through different binades), so it is used under WT_POS_EXACT only.
+static inline bool use_mirror(const wt_geom *g, int n) {
+    return g->positions == WT_POS_EXACT && n <= 2 && (size_t)g->rows * g->cols >= (size_t)768 * 768;
+}
 static inline int packed_images(const wt_geom *g, int n) { return use_mirror(g, n) ? 2 * n : chunk_of(n).v * chunk_of(n).groups; }
 
 // returns the number of per-image partial-sum slots the epilogue wrote (CTAs x passes), or a negative error
@@ -73,6 +77,8 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
     p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
     p.a_begin = a_begin; p.a_end = a_end;
+    p.warp = g->d_warp; p.astra = g->positions == WT_POS_ASTRA;
+    p.Ex = -0.5f * (float)g->cols + 0.5f; p.Ey = 0.5f * (float)g->rows - 0.5f;
     p.order = g->d_order; p.nphase = g->nphase;
     static const bool tile_major = [] { const char *e = getenv("WT_FP_ORDER"); return e && !strcmp(e, "tile"); }();
     if (tile_major) p.nphase = 0;   // A/B measurements only
@@ -119,7 +125,7 @@ template <class Epi>
 static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
                   cudaStream_t st) {
     BpParams p;
-    p.sp = sp; p.ang = g->d_bp;
+    p.sp = sp; p.ang = g->d_bp; p.fang = g->d_fp; p.warp = g->d_warp;
     p.R = g->rows; p.C = g->cols; p.A = g->nangles;
     p.padl = g->sino_padl; p.pitch = g->sino_pitch;
     p.a_begin = a_begin; p.a_end = a_end;
@@ -160,6 +166,7 @@ static unsigned g_slots_used[64] = {};   // bit i of entry d: slot i is taken on
 struct GeomPlan {
     std::vector<FpAngle> fp;
     std::vector<BpAngle> bp;
+    std::vector<WarpAngle> warp;
     std::vector<FpTile> tiles;
     std::vector<int> order;
     int phase_start[FP_MAX_PHASES + 1];
@@ -176,9 +183,38 @@ static int check_geometry(int rows, int cols, int ndet, float det_width, const f
     return WT_OK;
 }
 
-static void plan_geometry(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, GeomPlan &pl) {
+static int default_positions() {
+    const char *e = getenv("WT_POSITIONS");
+    return (e && !strcmp(e, "exact")) ? WT_POS_EXACT : WT_POS_ASTRA;
+}
+
+// The reference's float32 running sum as a position warp (common.cuh: WarpAngle): inside the binade [2^e, 2^(e+1)) a
+// float32 addition of delta advances the position by rint(delta / u) * u, u = 2^(e-23) (round half to even is what a
+// tie settles into after its first step).  A step that rounds to zero (|delta| < u/2: the reference's ray would stand
+// still there) keeps the nominal slope; such angles move by less than a pixel over the whole volume.
+static WarpAngle make_warp(float delta, int positions) {
+    WarpAngle w;
+    double g = 0.0;
+    for (int i = 0; i < WT_NB; ++i) {
+        double slope = 1.0;
+        if (positions == WT_POS_ASTRA && i > 0 && delta != 0.0f) {
+            const double u = ldexp(1.0, 5 + i - 23);
+            const double step = nearbyint((double)delta / u) * u;
+            if (step != 0.0) slope = (double)delta / step;
+        }
+        w.gcum[i] = g;
+        w.slope[i] = slope;
+        w.islope[i] = 1.0 / slope;
+        g += (stripe_pos(i + 1) - stripe_pos(i)) * slope;
+    }
+    return w;
+}
+
+static int plan_geometry(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, int positions,
+                         GeomPlan &pl) {
     pl.fp.assign(nangles, FpAngle());
     pl.bp.assign(nangles, BpAngle());
+    pl.warp.assign(nangles, WarpAngle());
     std::vector<FpAngle> &fp = pl.fp;
     std::vector<BpAngle> &bp = pl.bp;
     const double Ex = -0.5 * cols + 0.5, Ey = 0.5 * rows - 0.5;
@@ -193,7 +229,7 @@ static void plan_geometry(int rows, int cols, int ndet, float det_width, const f
         const int vertical = fabsf(ray_x) < fabsf(ray_y);
         FpAngle &f = fp[a];
         f.vertical = vertical;
-        f.pad_ = 0;
+        f.sx = sx; f.sy = sy; f.ux = ux; f.uy = uy;
         float ratio;
         if (vertical) {
             ratio = ray_x / ray_y;
@@ -209,6 +245,8 @@ static void plan_geometry(int rows, int cols, int ndet, float det_width, const f
             f.c0_step = -((double)uy - (double)ux * (double)ratio);
         }
         f.delta = -ratio;
+        f.ratio = ratio;
+        pl.warp[a] = make_warp(f.delta, positions);
         // gather form: pixel (line l, position k) sits at detector coordinate d* = (k - c0_base - l*delta)/c0_step - 0.5
         BpAngle &b = bp[a];
         const double inv = 1.0 / f.c0_step;
@@ -222,12 +260,23 @@ static void plan_geometry(int rows, int cols, int ndet, float det_width, const f
         b.pad_ = 0.0f;
     }
     // angle tiles of the forward projector: consecutive angles of one orientation whose rays, over any
-    // FP_DT-detector x FP_LB-line patch, stay within FP_WFIT positions of each other.  c_a - c_b is affine in
-    // (d, l), so the spread across angles is convex and peaks at a corner of the (d, l) rectangle.
+    // FP_DT-detector x FP_LB-line patch, stay within FP_WFIT positions of each other.  In exact arithmetic c_a - c_b is
+    // affine in (d, l), so the spread across angles peaks at a corner of the (d, l) rectangle; the reference's running
+    // sums bend the rays by up to a few positions (2.5 at 8192^2), piecewise linearly, so the spread is sampled on a
+    // 5 x 5 grid of the warped positions.
     std::vector<FpTile> &tiles = pl.tiles;
     tiles.clear();
     {
-        auto c_at = [&](int a, int d, int l) { return fp[a].c0_base + ((double)d + 0.5) * fp[a].c0_step + (double)l * fp[a].delta; };
+        auto c_at = [&](int a, double d, double l) {
+            const double c0 = fp[a].c0_base + (d + 0.5) * fp[a].c0_step;
+            return warp_ginv(pl.warp[a], warp_g(pl.warp[a], c0) + l * (double)fp[a].delta);
+        };
+        // a single angle's own spread over a CTA's patch must fit (wide detector pixels near 45 degrees do not)
+        for (int a = 0; a < nangles; ++a)
+            if ((FP_DT - 1) * fabs(fp[a].c0_step) + (FP_LB - 1) * fabs((double)fp[a].delta) > (double)FP_WFIT) {
+                g_err = "geometry: detector pixels too wide for the forward projector's staging window (det_width <~ 1.6)";
+                return WT_ERR_UNSUPPORTED;
+            }
         int a = 0;
         while (a < nangles) {
             int cnt = 1;
@@ -236,11 +285,13 @@ static void plan_geometry(int rows, int cols, int ndet, float det_width, const f
                 const int nl = fp[a].vertical ? rows : cols;
                 double worst = 0.0, ms = 0.0, md = 0.0;
                 for (int i = 0; i < n; ++i) { ms = fmax(ms, fabs(fp[a + i].c0_step)); md = fmax(md, fabs((double)fp[a + i].delta)); }
-                const int dc[2] = {0, ndet - 1}, lc[2] = {0, nl - 1};
-                for (int di = 0; di < 2; ++di)
-                    for (int li = 0; li < 2; ++li) {
+                for (int di = 0; di < 5; ++di)
+                    for (int li = 0; li < 5; ++li) {
                         double lo = 1e300, hi = -1e300;
-                        for (int i = 0; i < n; ++i) { const double c = c_at(a + i, dc[di], lc[li]); lo = fmin(lo, c); hi = fmax(hi, c); }
+                        for (int i = 0; i < n; ++i) {
+                            const double c = c_at(a + i, 0.25 * di * (ndet - 1), 0.25 * li * (nl - 1));
+                            lo = fmin(lo, c); hi = fmax(hi, c);
+                        }
                         worst = fmax(worst, hi - lo);
                     }
                 if (worst + (FP_DT - 1) * ms + (FP_LB - 1) * md > (double)FP_WFIT) break;
@@ -273,6 +324,7 @@ static void plan_geometry(int rows, int cols, int ndet, float det_width, const f
         }
         for (int i = nphase + 1; i <= FP_MAX_PHASES; ++i) phase_start[i] = phase_start[nphase];
     }
+    return WT_OK;
 }
 
 }  // namespace wt
@@ -292,10 +344,18 @@ long long wt_debug_oob_count(void) {
 }
 
 int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, wt_geom **out) {
+    return wt_geom_create_ex(rows, cols, ndet, det_width, angles, nangles, default_positions(), out);
+}
+
+int wt_geom_positions(const wt_geom *g) { return g ? g->positions : WT_ERR_INVALID; }
+
+int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float *angles, int nangles, int positions,
+                      wt_geom **out) {
     if (!out) return invalid("wt_geom_create: null pointer");
+    if (positions != WT_POS_ASTRA && positions != WT_POS_EXACT) return invalid("wt_geom_create: bad positions mode");
     if (int rc = check_geometry(rows, cols, ndet, det_width, angles, nangles, "wt_geom_create")) return rc;
     GeomPlan pl;
-    plan_geometry(rows, cols, ndet, det_width, angles, nangles, pl);
+    if (int rc = plan_geometry(rows, cols, ndet, det_width, angles, nangles, positions, pl)) return rc;
     const std::vector<FpAngle> &fp = pl.fp;
     const std::vector<BpAngle> &bp = pl.bp;
     const std::vector<FpTile> &tiles = pl.tiles;
@@ -304,14 +364,18 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     const int (&phase_start)[FP_MAX_PHASES + 1] = pl.phase_start;
     wt_geom *g = new wt_geom();
     g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
-    // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row
+    g->positions = positions;
+    // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row (the reference's
+    // running sums displace a pixel's detector coordinate by up to N * ulp(2N) / 2: 0.25 at 2048^2, 4 at 8192^2)
     const double halfdiag = 0.5 * sqrt((double)rows * rows + (double)cols * cols) / (double)det_width;
-    int padl = (int)ceil(halfdiag - (0.5 * ndet - 0.5)) + 3;
+    const double nmax = (double)(rows > cols ? rows : cols);
+    const int drift = positions == WT_POS_ASTRA ? (int)ceil(nmax * ldexp(2.0 * nmax, -24)) + 1 : 0;
+    int padl = (int)ceil(halfdiag - (0.5 * ndet - 0.5)) + 3 + drift;
     if (padl < 4) padl = 4;
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
     g->sino_pitch = (padl + ndet + padl + BP_SEGW_MAX + 3) & ~3;
-    g->d_fp = nullptr; g->d_bp = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
+    g->d_fp = nullptr; g->d_bp = nullptr; g->d_warp = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
     g->nphase = nphase;
     for (int i = 0; i <= FP_MAX_PHASES; ++i) g->phase_start[i] = phase_start[i];
     g->ntiles = (int)tiles.size();
@@ -323,6 +387,8 @@ int wt_geom_create(int rows, int cols, int ndet, float det_width, const float *a
     if (e == cudaSuccess) e = cudaMalloc(&g->d_bp, sizeof(BpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_fp, fp.data(), sizeof(FpAngle) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_bp, bp.data(), sizeof(BpAngle) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_warp, sizeof(WarpAngle) * nangles);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_warp, pl.warp.data(), sizeof(WarpAngle) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_tiles, sizeof(FpTile) * tiles.size());
     if (e == cudaSuccess) e = cudaMemcpy(g->d_tiles, tiles.data(), sizeof(FpTile) * tiles.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_order, sizeof(int) * order.size());
@@ -339,6 +405,7 @@ void wt_geom_destroy(wt_geom *g) {
     if (!g) return;
     if (g->d_fp) cudaFree(g->d_fp);
     if (g->d_bp) cudaFree(g->d_bp);
+    if (g->d_warp) cudaFree(g->d_warp);
     if (g->d_tiles) cudaFree(g->d_tiles);
     if (g->d_order) cudaFree(g->d_order);
     free(g->h_angles);
@@ -361,7 +428,7 @@ int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *ang
     if (!n_tiles) return invalid("wt_geom_plan: null pointer");
     if (int rc = check_geometry(rows, cols, ndet, det_width, angles, nangles, "wt_geom_plan")) return rc;
     GeomPlan pl;
-    plan_geometry(rows, cols, ndet, det_width, angles, nangles, pl);
+    if (int rc = plan_geometry(rows, cols, ndet, det_width, angles, nangles, default_positions(), pl)) return rc;
     const int nt = (int)pl.tiles.size();
     *n_tiles = nt;
     if (n_phases) *n_phases = pl.nphase;
@@ -394,6 +461,7 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angl
     Carver cv(ws, ws_bytes);
     float *vn = cv.take<float>(vn_floats(g, npack));
     float *vt = cv.take<float>(vt_floats(g, npack));
+    if (!cv.ok()) { g_err = "wt_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     HFpStore epi;
     epi.sino = sino;
     const int rc = run_fp(g, vol, nimages, angle_begin, angle_end, vn, vt, epi, (cudaStream_t)stream);
@@ -413,6 +481,7 @@ int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned
     float *vt = cv.take<float>(vt_floats(g, npack));
     cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);
     float *partial = cv.take<float>((size_t)3 * npack * fp_blocks(g));
+    if (!cv.ok()) { g_err = "wt_mar_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     HFpMar e;
     e.b = b; e.mask = mask; e.inv_ngood = inv_ngood; e.bt = bt; e.b_hb = b_hb; e.u = u; e.proj = proj;
     e.partial = stats ? partial : nullptr; e.nimg = nimages;
@@ -437,6 +506,7 @@ int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angl
     const int npack = packed_images(g, nimages);
     Carver cv(ws, ws_bytes);
     float *sp = cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);
+    if (!cv.ok()) { g_err = "wt_bp: workspace too small"; return WT_ERR_WORKSPACE; }
     HBpStore epi;
     epi.vol = vol;
     epi.scale = scale;
@@ -457,13 +527,14 @@ int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)g->nangles * g->ndet, img = (size_t)g->rows * g->cols;
     Carver cv(ws, ws_bytes);
-    const int npack = packed_images(g, nimages) < 2 ? 2 : packed_images(g, nimages);   // the W 1 / W^T 1 passes are 1 image
+    const int npack = packed_images(g, nimages);   // the one-image W 1 / W^T 1 passes never pack more than this
     float *vn = cv.take<float>(vn_floats(g, npack));
     float *vt = cv.take<float>(vt_floats(g, npack));
     float *sp = cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);
     float *raysum = cv.take<float>(plane);
     float *pixsum = cv.take<float>(img);
     float *resid = cv.take<float>((size_t)nimages * plane);
+    if (!cv.ok()) { g_err = "wt_sirt: workspace too small"; return WT_ERR_WORKSPACE; }
     // Rsum = W 1, Csum = W^T 1 (the residual buffer doubles as the all-ones input)
     fill_kernel<<<296, 256, 0, st>>>(vol, img, 1.0f);
     HFpStore fs; fs.sino = raysum;
@@ -540,6 +611,7 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
     float *vt = cv.take<float>(vt_floats(g, npack));
     float *sp = cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);  // generic-K path: holds P (n, A, D)
     float *partial = cv.take<float>((size_t)npack * fp_blocks(g));
+    if (!cv.ok()) { g_err = "wt_white_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     int nb = 0;
     if (K == 1 || K == 2) {
         nb = fp_blocks(g);

@@ -52,6 +52,8 @@ inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int
 struct BpParams {
     const float *sp;  // packed sinogram (G, A, pitch, V)
     const BpAngle *ang;
+    const FpAngle *fang;     // the forward projector's constants of the same angles (c0_base, c0_step, delta)
+    const WarpAngle *warp;   // per angle: the reference's running sum as a position warp (identity under WT_POS_EXACT)
     int R, C, A;
     int nimg;         // images of this launch; the last group is padded with zero components up to V
     int Rproc;        // rows that get a thread: R, or ceil(R/2) under mirror pairing
@@ -91,8 +93,8 @@ template <int V, int TH>
 struct BpSmem {
     typedef typename VecOf<V>::T VecT;
     VecT seg[BP_STAGES][BP_AB][BpTile<TH>::SEGW];
-    float4 cst[BP_STAGES][BP_AB];  // dcol, drow, base - 1/2, Ah = A0 - B/2
-    float2 cst2[BP_STAGES][BP_AB]; // B, unused
+    float4 cst[BP_STAGES][BP_AB];  // affine piece A of d*: dcol, drow, base - 1/2;  Ah = A0 - B/2
+    float4 cst2[BP_STAGES][BP_AB]; // affine piece B of d*: dcol, drow, base - 1/2;  B (negative: d* = min(A, B), else max)
     uint64_t full[BP_STAGES];   // TMA bytes of a stage have landed
     uint64_t empty[BP_STAGES];  // all consumer warps are done reading a stage
 };
@@ -100,7 +102,7 @@ struct BpSmem {
 // Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
 // MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
 template <int V, class Epi, bool MIRROR, int TH>
-__global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
+__global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     constexpr int BP_TH = TH, BP_RPT = BpTile<TH>::RPT, BP_SEGW = BpTile<TH>::SEGW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -129,16 +131,84 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         const VecT *src = nullptr;
         if (lane < nvalid) {
+            // Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
+            //     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
+            // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two
+            // from 64 on), so z = G(k) - l * delta is affine over the tile.  Ginv is piecewise affine in z with kinks
+            // where a ray STARTED on a binade boundary; the tile's z-range (< 97 wide) usually holds none, sometimes one
+            // that matters: d* is then the max (or min) of two affine pieces, which is what the consumers evaluate.
             const BpAngle an = p.ang[a];
-            const double d_t00 = an.d00 + (double)col0 * an.dcol + (double)row0 * an.drow;
-            const double dmin = d_t00 + fmin(0.0, (double)(tw - 1) * an.dcol) + fmin(0.0, (double)(th - 1) * an.drow);
+            const FpAngle fa = p.fang[a];
+            const WarpAngle *w = p.warp + a;
+            const bool vert = fa.vertical != 0;
+            const int k0 = vert ? col0 : row0, l0 = vert ? row0 : col0;
+            const int nk = vert ? tw : th, nl = vert ? th : tw;
+            const int ik = stripe_of((double)k0);
+            const double sk = __ldg(&w->slope[ik]);
+            const double gk0 = __ldg(&w->gcum[ik]) + ((double)k0 - stripe_pos(ik)) * sk;
+            const double dl = (double)fa.delta;
+            const double za = gk0 - (double)l0 * dl, zk = sk * (double)(nk - 1), zl = -dl * (double)(nl - 1);
+            const double zlo = za + fmin(0.0, zk) + fmin(0.0, zl), zhi = za + fmax(0.0, zk) + fmax(0.0, zl);
+            const double zc = 0.5 * (zlo + zhi);
+            // piece A: the stripe of the tile centre; piece B: across the kink inside (zlo, zhi) that bends d* most
+            int ia = 0;
+            for (int j = 1; j < WT_NB; ++j)
+                if (fabs(zc) >= __ldg(&w->gcum[j])) ia = j;
+            const double sgn_a = zc < 0.0 ? -1.0 : 1.0;
+            int ib = ia;
+            double sgn_b = sgn_a, worst = 0.0;
+            bool b_high = false;                                               // piece B lies at larger z than the centre
+            for (int j = 1; j < WT_NB; ++j) {
+                const double gb = __ldg(&w->gcum[j]);
+                const double bend = fabs(__ldg(&w->islope[j]) - __ldg(&w->islope[j - 1]));
+                for (int sg = 0; sg < 2; ++sg) {
+                    const double zb = sg ? -gb : gb;
+                    if (zb <= zlo || zb >= zhi) continue;
+                    const double far_side = zb > zc ? zhi - zb : zb - zlo;     // extent on the side away from the centre
+                    if (bend * far_side > worst) {
+                        worst = bend * far_side;
+                        // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
+                        const bool outward = sg ? (zb < zc) : (zb > zc);
+                        ib = outward ? j : j - 1;
+                        sgn_b = sg ? -1.0 : 1.0;
+                        b_high = zb > zc;
+                    }
+                }
+            }
+            // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i
+            const double inv_step = 1.0 / fa.c0_step;
+            auto piece = [&](double sgn, int i, double &d_t00, double &dk, double &dll) {
+                const double isl = __ldg(&w->islope[i]);
+                d_t00 = (sgn * stripe_pos(i) + (za - sgn * __ldg(&w->gcum[i])) * isl - fa.c0_base) * inv_step - 0.5;
+                dk = sk * isl * inv_step;
+                dll = -dl * isl * inv_step;
+            };
+            double tA, kA, lA, tB, kB, lB;
+            piece(sgn_a, ia, tA, kA, lA);
+            piece(sgn_b, ib, tB, kB, lB);
+            // beyond the kink piece B is the right one: d* = max(A, B) if B lies above A there, else min(A, B)
+            const double kf = (double)(nk - 1), lf = (double)(nl - 1);
+            double dmin = 1e300;
+            bool use_max = true;
+            {
+                // corner of the tile furthest into B's side in z
+                const double ck = (zk > 0.0) == b_high ? kf : 0.0, cl = (zl > 0.0) == b_high ? lf : 0.0;
+                use_max = (tB + ck * kB + cl * lB) >= (tA + ck * kA + cl * lA);
+            }
+            for (int c = 0; c < 4; ++c) {
+                const double ck = (c & 1) ? kf : 0.0, cl = (c & 2) ? lf : 0.0;
+                const double va = tA + ck * kA + cl * lA, vb = tB + ck * kB + cl * lB;
+                dmin = fmin(dmin, use_max ? fmax(va, vb) : fmin(va, vb));
+            }
             const int lo = (int)floor(dmin) - 1 + p.padl;  // >= 0 by construction of padl
             const int aligned = lo & ~3;
             // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
-            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
-            sm.cst[s][lane] = make_float4((float)an.dcol, (float)an.drow,
-                                          (float)(d_t00 + (double)(p.padl - aligned) - 0.5), an.a0 - 0.5f * an.b);
-            sm.cst2[s][lane] = make_float2(an.b, 0.0f);
+            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2).  B = len * |dc/dd| at
+            // fixed line: the rays' spacing on the line, stretched by the warp between their start and the tile.
+            const float bw = (float)((double)an.b * (__ldg(&w->slope[ia]) / sk));
+            const double off = (double)(p.padl - aligned) - 0.5;
+            sm.cst[s][lane] = make_float4((float)(vert ? kA : lA), (float)(vert ? lA : kA), (float)(tA + off), an.a0 - 0.5f * bw);
+            sm.cst2[s][lane] = make_float4((float)(vert ? kB : lB), (float)(vert ? lB : kB), (float)(tB + off), use_max ? bw : -bw);
             src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
         }
         __syncwarp();
@@ -226,18 +296,24 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         if constexpr (POS) tap_triple_fma<V>(wa, v0, wb, v1, wc, vx, a1);
         else tap_triple_fma<V>(wa, vx, wb, v0, wc, v1, a1);
     };
-    auto one_angle = [&](auto pos_tag, const float4 &c4, float bw, const VecT *seg) {
+    // d* of a pixel = max or min of the angle's two affine pieces (one FMNMX with a uniform predicate)
+    auto one_angle = [&](auto pos_tag, const float4 &c4, const float4 &c5, bool use_max, float bw, const VecT *seg) {
+        auto dstar = [&](float j, float i) {
+            const float a = fmaf(j, c4.x, fmaf(i, c4.y, c4.z)), b = fmaf(j, c5.x, fmaf(i, c5.y, c5.z));
+            return use_max ? fmaxf(a, b) : fminf(a, b);
+        };
 #pragma unroll
         for (int j = 0; j < BP_RPT / 2; ++j) {
-            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z);
+            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z), dr0b = fmaf(ir[2 * j], c5.y, c5.z);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float ds0 = fmaf(jc[c], c4.x, dr0);
+                const float da = fmaf(jc[c], c4.x, dr0), db = fmaf(jc[c], c5.x, dr0b);
+                const float ds0 = use_max ? fmaxf(da, db) : fminf(da, db);
                 if (2 * j + c < BpShare<V>::value) {
                     shared_pair(pos_tag, ds0, c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
                 } else {
                     single(ds0, c4, bw, seg, acc[2 * j][c]);
-                    single(fmaf(jc[c], c4.x, fmaf(ir[2 * j + 1], c4.y, c4.z)), c4, bw, seg, acc[2 * j + 1][c]);
+                    single(dstar(jc[c], ir[2 * j + 1]), c4, bw, seg, acc[2 * j + 1][c]);
                 }
             }
         }
@@ -248,11 +324,12 @@ __global__ void __launch_bounds__(BP_BLOCK) bp_kernel(BpParams p, Epi epi) {
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
-            const float4 c4 = sm.cst[s][k];
-            const float bw = sm.cst2[s][k].x;
+            const float4 c4 = sm.cst[s][k], c5 = sm.cst2[s][k];
+            const float bw = fabsf(c5.w);
+            const bool use_max = c5.w >= 0.0f;
             const VecT *seg = &sm.seg[s][k][0];
-            if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), c4, bw, seg);
-            else one_angle(std::false_type(), c4, bw, seg);
+            if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), c4, c5, use_max, bw, seg);
+            else one_angle(std::false_type(), c4, c5, use_max, bw, seg);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s

@@ -40,13 +40,17 @@ constexpr int BP_BLOCK = BP_THREADS + 32;  // + one producer warp that only driv
 // FP: position along the interpolation axis for line l and detector d is
 //     c(l, d) = c0_base + (d + 0.5) * c0_step + l * delta        (ASTRA linear projector)
 // with the float32 vector-geometry fields ASTRA would hold, combined in double once per ray.
+// The float32 fields themselves (sx .. ratio) let the kernel repeat ASTRA's own float32 evaluation of the position
+// at line 0 operation by operation (WT_POS_ASTRA, see fp.cuh).
 struct FpAngle {
     double c0_base;
     double c0_step;
     float delta;    // tan(theta) (vertical) or cot(theta) (horizontal), float32 like the reference
     float len;      // 1/|cos| or 1/|sin|
     int vertical;   // |ray_x| < |ray_y| evaluated on float32 values
-    int pad_;
+    float sx, sy;   // detector start  (float32 fields of ASTRA's vector geometry)
+    float ux, uy;   // detector step
+    float ratio;    // ray_x / ray_y (vertical) or ray_y / ray_x (horizontal)
 };
 
 // BP (gather form of the exact transpose, SURVEY A.3, derived from the same FpAngle so that
@@ -61,6 +65,47 @@ struct BpAngle {
     float pad_;
 };
 
+// ---- the reference's float32 running sum as a position warp (WT_POS_ASTRA) ----------------------------------------
+// ASTRA advances a ray's position with a float32 running sum, c += delta once per line (SURVEY A.2;
+// oracle/astra_linear.c:93,120).  While |c| stays inside one binade [2^e, 2^(e+1)) every addition rounds to that
+// binade's grid u = 2^(e-23), so the ray does not advance by delta but by step_e = rint(delta / u) * u: its speed
+// depends on WHERE it is, not on which ray it is.  Integrating dc/dl = step(|c|) gives the "unwarped" coordinate
+//     G(c) = int_0^c delta / step(|c'|) dc'      (odd, piecewise linear, slope 1 for |c| < 64, kinks at +-2^e)
+// in which every ray moves at the nominal speed again:  G(c_l) = G(c_0) + l * delta.  The reference's position is
+// therefore  c_l(d) = Ginv(G(c_0(d)) + l * delta)  up to the O(u) discretisation at the <= 12 binade crossings of a
+// ray (measured: 1.5e-4 pixel rms at N = 2048 and 3e-4 at N = 8192, where the plain closed form c_0 + l * delta is
+// 3e-2 resp. 0.6 pixel rms -- up to 2.5 pixel -- away from what the reference computes).  K1 uses the table for its
+// staging windows and line ranges (its positions themselves repeat the float32 sum literally); K2 inverts the map:
+// the detector coordinate of pixel (line l, position k) is  d* = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
+// Under WT_POS_EXACT every slope is 1 and G is the identity.
+constexpr int WT_NB = 11;   // stripes of |position|: [0, 64), [64, 128), ..., [2^15, inf)
+struct WarpAngle {
+    double gcum[WT_NB];     // G at the lower edge of stripe i (gcum[0] = 0)
+    double slope[WT_NB];    // dG/dc inside stripe i = delta / step_i
+    double islope[WT_NB];   // 1 / slope
+};
+__host__ __device__ inline double stripe_pos(int i) { return i == 0 ? 0.0 : (double)(32 << i); }
+__host__ __device__ inline int stripe_of(double a) {   // a >= 0
+    int i = 0;
+    for (int j = 1; j < WT_NB; ++j)
+        if (a >= (double)(32 << j)) i = j;
+    return i;
+}
+__host__ __device__ inline double warp_g(const WarpAngle &w, double c) {
+    const double a = fabs(c);
+    const int i = stripe_of(a);
+    const double g = w.gcum[i] + (a - stripe_pos(i)) * w.slope[i];
+    return c < 0.0 ? -g : g;
+}
+__host__ __device__ inline double warp_ginv(const WarpAngle &w, double z) {
+    const double a = fabs(z);
+    int i = 0;
+    for (int j = 1; j < WT_NB; ++j)
+        if (a >= w.gcum[j]) i = j;
+    const double c = stripe_pos(i) + (a - w.gcum[i]) * w.islope[i];
+    return z < 0.0 ? -c : c;
+}
+
 }  // namespace wt
 
 struct wt_geom {
@@ -70,6 +115,8 @@ struct wt_geom {
     int sino_pitch;  // packed sinogram row pitch in detector positions (multiple of 4)
     wt::FpAngle *d_fp;
     wt::BpAngle *d_bp;
+    wt::WarpAngle *d_warp;   // per angle: the reference's float32 running sum as a position warp (identity under WT_POS_EXACT)
+    int positions;           // WT_POS_ASTRA | WT_POS_EXACT
     void *d_tiles;   // wt::FpTile[ntiles]: angle tiles of the forward projector
     int ntiles;
     int *d_order;    // launch order of the tiles, phase by phase (fp.cuh: fp_block)

@@ -16,6 +16,13 @@
 // 128 B/clk/SM.  (The first version of this kernel gathered through L1 with __ldg: a warp's 32 adjacent
 // detectors span 5-7 cache lines per load and ncu showed l1tex at 98% with 2.3x the minimum wavefronts;
 // see profiles/r1_ncu_full_v1_summary.txt.)
+//
+// Positions.  WT_POS_ASTRA (default): every thread repeats the reference's float32 arithmetic literally -- the
+// position at line 0 with ASTRA's own sequence of float32 operations, then one float32 addition per line from line 0
+// on (oracle/astra_linear.c:88-93,119-120), including the lines before the ray enters the volume (a serial chain of
+// FADDs in the prologue: 0.26 N^2 A additions against 11.7 N^2 A instructions of gather work).  The staging windows
+// and line ranges come from the same sum in its warped closed form (common.cuh: WarpAngle).  WT_POS_EXACT and the
+// mirror-paired kernels evaluate c_0 + l * delta per chunk (float64 bases).
 #pragma once
 #include "common.cuh"
 
@@ -36,7 +43,8 @@ constexpr int FP_W = 96;        // positions per staged line window
 constexpr int FP_STAGES = WT_FP_STAGES;
 // budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
 // for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
-constexpr int FP_WFIT = FP_W - 8;
+// (the 9th position of the margin absorbs the residual of the warped closed form that places the windows)
+constexpr int FP_WFIT = FP_W - 9;
 constexpr int FP_MAX_PHASES = 4;
 
 __host__ __device__ inline int fp_pitch(int npos) {
@@ -119,6 +127,9 @@ struct FpParams {
     int nimg;          // images of this launch; the last group is padded with zero components up to V
     int Dproc;         // detectors that get a thread: D, or ceil(D/2) under mirror pairing
     int a_begin, a_end;
+    const WarpAngle *warp;   // per angle (identity under WT_POS_EXACT)
+    int astra;               // 1: positions are the reference's float32 running sums (WT_POS_ASTRA)
+    float Ex, Ey;            // -C/2 + 1/2, R/2 - 1/2 as float32 (ASTRA's volume corner)
     // CTA launch order (see fp_block): tiles grouped into phases (one per orientation)
     const int *order;  // tile indices, phase by phase
     int nphase;
@@ -181,9 +192,30 @@ struct FpSmem {
     uint64_t full[FP_STAGES];   // TMA bytes of a stage have landed
     uint64_t empty[FP_STAGES];  // all consumer warps are done reading a stage
     float wstart[FP_STAGES];
-    float cmin[FP_AT], cmax[FP_AT], delta[FP_AT];  // per angle of the tile: position range at line 0, slope
+    float zmin[FP_AT], delta[FP_AT];   // per angle of the tile: left-most ray at line 0 in unwarped coordinates, slope
+    float gcum[FP_AT][WT_NB], islope[FP_AT][WT_NB];   // the angles' position warps (float copies)
     int lo, hi;                                    // line range any ray of the CTA needs
 };
+
+// float versions of warp_g / warp_ginv over the shared-memory copy of one angle's table
+__device__ __forceinline__ float warp_g_f(const float *gcum, const float *islope, float c) {
+    const float a = fabsf(c);
+    int i = 0;
+#pragma unroll
+    for (int j = 1; j < WT_NB; ++j)
+        if (a >= (float)(32 << j)) i = j;
+    const float pos = i ? (float)(32 << i) : 0.0f;
+    return copysignf(gcum[i] + __fdividef(a - pos, islope[i]), c);
+}
+__device__ __forceinline__ float warp_ginv_f(const float *gcum, const float *islope, float z) {
+    const float a = fabsf(z);
+    int i = 0;
+#pragma unroll
+    for (int j = 1; j < WT_NB; ++j)
+        if (a >= gcum[j]) i = j;
+    const float pos = i ? (float)(32 << i) : 0.0f;
+    return copysignf(fmaf(a - gcum[i], islope[i], pos), z);
+}
 
 // Epilogue contract: epi.operator()<W>(p, g, a, d, valid, val[W], cta_scratch, pass, npass) handles the W images of
 // group g (image index g*W + i) for ray (a, d); it is called by ALL threads of the CTA (it may synchronise).  Under
@@ -226,25 +258,26 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         sm.hi = 0;
     }
     if (tid < FP_AT) {
-        // position range of the tile's rays of this angle at line 0 (detectors d0 .. min(d0+DT, D)-1)
-        float lo_c = 3.0e38f, hi_c = -3.0e38f, dl = 0.0f;
+        // this angle's position warp, and the left-most of the tile's rays of this angle at line 0 (detectors
+        // d0 .. min(d0+DT, D)-1) in unwarped coordinates (G is increasing: the left-most ray stays the left-most)
+        float lo_z = 3.0e38f, dl = 0.0f;
         const int aa = tile.first + tid;
         if (tid < tile.count) {
             const FpAngle an = p.ang[aa];
+            const WarpAngle *w = p.warp + aa;
+            for (int i = 0; i < WT_NB; ++i) { sm.gcum[tid][i] = (float)__ldg(&w->gcum[i]); sm.islope[tid][i] = (float)__ldg(&w->islope[i]); }
             const int dl_ = min(d0 + FP_DT, p.Dproc) - 1;
             const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
             const double cb = an.c0_base + ((double)dl_ + 0.5) * an.c0_step;
-            lo_c = (float)fmin(ca, cb);
-            hi_c = (float)fmax(ca, cb);
+            lo_z = warp_g_f(sm.gcum[tid], sm.islope[tid], (float)fmin(ca, cb));
             dl = an.delta;
         }
-        sm.cmin[tid] = lo_c;
-        sm.cmax[tid] = hi_c;
+        sm.zmin[tid] = lo_z;
         sm.delta[tid] = dl;
     }
     __syncthreads();
 
-    float c0h = 0.0f, delta = 0.0f, len = 0.0f;
+    float c0h = 0.0f, delta = 0.0f, len = 0.0f, c_run = 0.0f;
     int l_lo = 0, l_hi = 0;
     if (intile) {
         const FpAngle an = p.ang[a];
@@ -252,15 +285,26 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         delta = an.delta;
         len = an.len;
         c0h = c0 - 0.5f;
-        // lines on which floor(c) can be inside [-1, npos-1]; the estimate may be off by one line on each side,
-        // which the zero padding absorbs (|delta| <= 1, VPAD = 4)
+        if (p.astra) {
+            // the reference's float32 evaluation of the position at line 0, operation by operation
+            // (oracle/astra_linear.c:88-92,119; no contraction)
+            const float dh = __fadd_rn((float)d, 0.5f);
+            const float Dx = __fadd_rn(an.sx, __fmul_rn(dh, an.ux)), Dy = __fadd_rn(an.sy, __fmul_rn(dh, an.uy));
+            if (an.vertical) c_run = __fsub_rn(__fadd_rn(Dx, __fmul_rn(__fsub_rn(p.Ey, Dy), an.ratio)), p.Ex);
+            else c_run = -__fsub_rn(__fadd_rn(Dy, __fmul_rn(__fsub_rn(p.Ex, Dx), an.ratio)), p.Ey);
+        }
+        // lines on which floor(c) can be inside [-1, npos-1], from the warped closed form G(c_l) = G(c_0) + l delta;
+        // the estimate may be off by a line on each side (and by the 5e-3 pixel residual of the warp), which the
+        // zero padding absorbs (|delta| <= 1, VPAD = 4)
+        const float *gc = sm.gcum[slot], *is = sm.islope[slot];
+        const float z0 = warp_g_f(gc, is, c0), zn = warp_g_f(gc, is, (float)npos);
         if (fabsf(delta) * (float)nlines < 0.5f) {
             const bool hit = (c0 > -2.0f) && (c0 < (float)npos + 1.0f);
             l_lo = 0;
             l_hi = hit ? nlines : 0;
         } else {
             const float inv = 1.0f / delta;
-            const float t0 = (-1.0f - c0) * inv, t1 = ((float)npos - c0) * inv;
+            const float t0 = (-1.05f - z0) * inv, t1 = (zn + 0.05f - z0) * inv;
             l_lo = (int)fmaxf(floorf(fminf(t0, t1)), 0.0f);
             l_hi = (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)nlines);
         }
@@ -285,8 +329,10 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         // left-most position any ray of the tile takes on these lines (linear in l: attained at an end)
         float m = 3.0e38f;
         if (lane < FP_AT) {
-            const float cm = sm.cmin[lane], dl = sm.delta[lane];
-            if (cm < 1.0e38f) m = fminf(fmaf((float)l0, dl, cm), fmaf((float)l1, dl, cm));
+            const float zm = sm.zmin[lane], dl = sm.delta[lane];
+            if (zm < 1.0e38f)
+                m = fminf(warp_ginv_f(sm.gcum[lane], sm.islope[lane], fmaf((float)l0, dl, zm)),
+                          warp_ginv_f(sm.gcum[lane], sm.islope[lane], fmaf((float)l1, dl, zm)));
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -319,6 +365,42 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         for (int ch = 0; ch < nchunk; ++ch) {
             if (ch >= FP_STAGES) mbar_wait(&sm.empty[ch % FP_STAGES], (uint32_t)(((ch / FP_STAGES) - 1) & 1));
             produce(ch);
+        }
+    } else if (!MIRROR && p.astra) {
+        // the reference's running sum: c at line l is c_0 after l float32 additions of delta.  Lines before the ray
+        // enters the volume are skipped by doing just the additions.
+        if (nchunk > 0) {
+#pragma unroll 8
+            for (int l = 0; l < l_lo; ++l) c_run += delta;
+        }
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int s = ch % FP_STAGES;
+            mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
+            const int l0 = Lb + ch * FP_LB;
+            const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
+            if (la < lb) {
+                // c - 1/2 relative to the window start: window starts are integers, so the difference of two float32
+                // values a few positions apart is exact
+                const float wsh = sm.wstart[s] + 0.5f;
+                const VecT *row = &sm.seg[s][la - l0][0];
+#pragma unroll 4
+                for (int l = la; l < lb; ++l) {
+                    const float cr = c_run - wsh;
+                    const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
+                    const float off = (cr - (t - MAGIC)) + 0.5f;
+                    const int idx = __float_as_int(t) - MAGIC_BITS;
+                    check_index(idx, idx + 1, FP_W);
+                    float v0[V], v1[V];
+                    unpack<V>(row[idx], v0);
+                    unpack<V>(row[idx + 1], v1);
+                    const float w0 = 1.0f - off;
+                    tap_pair_fma<V>(off, v1, w0, v0, acc);
+                    c_run += delta;
+                    row += FP_W;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with stage s
         }
     } else {
         for (int ch = 0; ch < nchunk; ++ch) {

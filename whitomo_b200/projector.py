@@ -65,7 +65,11 @@ class Spectrum(object):
 
 
 class Projector(object):
-    def __init__(self, rows, cols, ndet, angles, det_width=1.0, device=None):
+    """``positions``: "astra" (default; the reference's float32 running-sum ray positions, include/whitomo_b200.h
+    WT_POS_ASTRA) or "exact" (closed-form positions, mirror-paired single-image kernels); None reads the environment
+    variable WT_POSITIONS."""
+
+    def __init__(self, rows, cols, ndet, angles, det_width=1.0, device=None, positions=None):
         _require_cuda()
         self.lib = _capi.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -73,11 +77,18 @@ class Projector(object):
         self.det_width = float(det_width)
         self.angles = np.ascontiguousarray(np.asarray(angles, dtype=np.float64).astype(np.float32))
         self.nangles = int(self.angles.shape[0])
+        if positions is None:
+            import os
+            positions = os.environ.get("WT_POSITIONS", "astra") or "astra"
+        if positions not in ("astra", "exact"):
+            raise ValueError("positions must be 'astra' or 'exact'")
+        self.positions = positions
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.wt_geom_create(self.rows, self.cols, self.ndet, self.det_width,
-                                                self.angles.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
-                                                self.nangles, ctypes.byref(h)))
+            _capi.check(self.lib.wt_geom_create_ex(self.rows, self.cols, self.ndet, self.det_width,
+                                                   self.angles.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                                   self.nangles, _capi.POS_EXACT if positions == "exact" else _capi.POS_ASTRA,
+                                                   ctypes.byref(h)))
         self.handle = h
         self._ws = {}
 
