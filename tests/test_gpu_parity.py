@@ -331,6 +331,27 @@ def test_wide_detector_pixels_and_unordered_angles(eng, det_width):
     assert np.array_equal(p[:, 4], p[:, 5])                # the repeated view
 
 
+def test_wide_detector_pixels_on_a_volume_wider_than_the_staging_window(eng):
+    """det_width = 1.5 on 300 x 260 (lines longer than K1's 96-position window, so the window really slides): parity;
+    det_width = 2 near 45 degrees spreads one angle's 32 detectors x 16 lines over more than the window holds:
+    the geometry is refused (WT_ERR_UNSUPPORTED) instead of being projected wrongly"""
+    Projector, _ = eng
+    from whitomo_b200._capi import EngineError
+    r, c, d = 300, 260, 301
+    ang = np.linspace(0, np.pi, 37)
+    g = oracle.Geometry(r, c, d, ang, det_width=1.5)
+    P = Projector(r, c, d, ang, det_width=1.5)
+    x = np.stack([phantom(r, c, s) for s in range(3)])
+    y = np.random.default_rng(9).random((3,) + g.sino_shape).astype(np.float32)
+    p = P.fp(torch.from_numpy(x).cuda()).cpu().numpy()
+    v = P.bp(torch.from_numpy(y).cuda()).cpu().numpy()
+    for i in range(3):
+        assert rel_l2(p[i], oracle.fp(g, x[i])) < TOL_OP
+        assert rel_l2(v[i], oracle.bp(g, y[i])) < TOL_OP
+    with pytest.raises(EngineError, match="too wide"):
+        Projector(r, c, d, ang, det_width=2.0)
+
+
 def test_repeated_calls_are_bit_identical(eng):
     """the TMA / mbarrier pipelines hand stages between a producer warp and 8 consumer warps with no other
     synchronisation; a hand-off race would show up as run-to-run differences"""

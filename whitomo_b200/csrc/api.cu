@@ -190,17 +190,17 @@ static int default_positions() {
 
 // The reference's float32 running sum as a position warp (common.cuh: WarpAngle): inside the binade [2^e, 2^(e+1)) a
 // float32 addition of delta advances the position by rint(delta / u) * u, u = 2^(e-23) (round half to even is what a
-// tie settles into after its first step).  A step that rounds to zero (|delta| < u/2: the reference's ray would stand
-// still there) keeps the nominal slope; such angles move by less than a pixel over the whole volume.
+// tie settles into after its first step).  Where the step rounds to zero (|delta| < u/2) the reference's ray stands
+// still: G gets a huge slope there, so rays neither leave such a stripe nor travel into it beyond its edge.
 static WarpAngle make_warp(float delta, int positions) {
     WarpAngle w;
     double g = 0.0;
     for (int i = 0; i < WT_NB; ++i) {
         double slope = 1.0;
         if (positions == WT_POS_ASTRA && i > 0 && delta != 0.0f) {
-            const double u = ldexp(1.0, 5 + i - 23);
+            const double u = ldexp(1.0, 1 + i - 23);          // stripe i = binade [2^(i+1), 2^(i+2))
             const double step = nearbyint((double)delta / u) * u;
-            if (step != 0.0) slope = (double)delta / step;
+            slope = step != 0.0 ? (double)delta / step : WT_STUCK_SLOPE;
         }
         w.gcum[i] = g;
         w.slope[i] = slope;
@@ -271,9 +271,11 @@ static int plan_geometry(int rows, int cols, int ndet, float det_width, const fl
             const double c0 = fp[a].c0_base + (d + 0.5) * fp[a].c0_step;
             return warp_ginv(pl.warp[a], warp_g(pl.warp[a], c0) + l * (double)fp[a].delta);
         };
-        // a single angle's own spread over a CTA's patch must fit (wide detector pixels near 45 degrees do not)
+        // a single angle's own spread over a CTA's patch must fit (wide detector pixels near 45 degrees do not),
+        // unless the staged window holds every in-volume position of a line wherever it starts
         for (int a = 0; a < nangles; ++a)
-            if ((FP_DT - 1) * fabs(fp[a].c0_step) + (FP_LB - 1) * fabs((double)fp[a].delta) > (double)FP_WFIT) {
+            if ((fp[a].vertical ? cols : rows) > FP_W - VPAD - 1 &&
+                (FP_DT - 1) * fabs(fp[a].c0_step) + (FP_LB - 1) * fabs((double)fp[a].delta) > (double)FP_WFIT) {
                 g_err = "geometry: detector pixels too wide for the forward projector's staging window (det_width <~ 1.6)";
                 return WT_ERR_UNSUPPORTED;
             }

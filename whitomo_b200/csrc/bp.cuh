@@ -94,10 +94,20 @@ struct BpSmem {
     typedef typename VecOf<V>::T VecT;
     VecT seg[BP_STAGES][BP_AB][BpTile<TH>::SEGW];
     float4 cst[BP_STAGES][BP_AB];  // affine piece A of d*: dcol, drow, base - 1/2;  Ah = A0 - B/2
-    float4 cst2[BP_STAGES][BP_AB]; // affine piece B of d*: dcol, drow, base - 1/2;  B (negative: d* = min(A, B), else max)
+    float4 cst2[BP_STAGES][BP_AB]; // affine piece B of d*: dcol, drow, base - 1/2;  Ah of piece B
+    float4 cst3[BP_STAGES][BP_AB]; // B of piece A, B of piece B, flags (BP_F_*), unused
     uint64_t full[BP_STAGES];   // TMA bytes of a stage have landed
     uint64_t empty[BP_STAGES];  // all consumer warps are done reading a stage
 };
+
+// How the consumers treat an angle of a stage (uniform over the CTA):
+//   0            one affine piece, rays at least a position apart: two taps per pixel, pairs share taps (the fast path)
+//   BP_F_KINK    two pieces whose slopes differ by < 3e-4 (a kink of the position warp crosses the tile): the fast path
+//                with d* = max | min of the pieces (BP_F_MIN)
+//   BP_F_GENERIC two pieces of clearly different slope and/or
+//   BP_F_FOUR    rays less than a position apart on the pixel line (the warp compresses them): up to three rays reach a
+//                pixel, so four candidate taps are weighted.  Every pixel is located on its own (the generic path).
+constexpr int BP_F_GENERIC = 1, BP_F_MIN = 2, BP_F_FOUR = 4, BP_F_KINK = 8;
 
 // Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
 // MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
@@ -133,34 +143,45 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         if (lane < nvalid) {
             // Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
             //     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
-            // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two
-            // from 64 on), so z = G(k) - l * delta is affine over the tile.  Ginv is piecewise affine in z with kinks
-            // where a ray STARTED on a binade boundary; the tile's z-range (< 97 wide) usually holds none, sometimes one
-            // that matters: d* is then the max (or min) of two affine pieces, which is what the consumers evaluate.
+            // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two;
+            // over positions [0, 64) G is replaced by its secant, see below), so
+            // z = G(k) - l * delta is affine over the tile.  Ginv is piecewise affine in z with kinks where a ray
+            // STARTED on a binade boundary; the tile's z-range (< 97 wide) usually holds none that matters (2-7 % of
+            // the tile x angle pairs at 8192^2 do): d* is then the max (or min) of two affine pieces.
             const BpAngle an = p.ang[a];
             const FpAngle fa = p.fang[a];
             const WarpAngle *w = p.warp + a;
+            // K2's view of the warp: the stripes below 64 merged into one with the secant slope G(64) / 64 (used for G
+            // and Ginv alike, so the two stay inverse to each other): merged stripe 0 = [0, 64), m >= 1 = stripe m + 4
+            constexpr int NM = WT_NB - 4;
+            const double s0 = __ldg(&w->gcum[5]) * (1.0 / 64.0);
+            auto m_pos = [&](int m) { return m ? stripe_pos(m + 4) : 0.0; };
+            auto m_cum = [&](int m) { return m ? __ldg(&w->gcum[m + 4]) : 0.0; };
+            auto m_slope = [&](int m) { return m ? __ldg(&w->slope[m + 4]) : s0; };
+            auto m_isl = [&](int m) { return m ? __ldg(&w->islope[m + 4]) : 1.0 / s0; };
             const bool vert = fa.vertical != 0;
             const int k0 = vert ? col0 : row0, l0 = vert ? row0 : col0;
             const int nk = vert ? tw : th, nl = vert ? th : tw;
-            const int ik = stripe_of((double)k0);
-            const double sk = __ldg(&w->slope[ik]);
-            const double gk0 = __ldg(&w->gcum[ik]) + ((double)k0 - stripe_pos(ik)) * sk;
+            int ik = 0;
+            for (int m = 1; m < NM; ++m)
+                if ((double)k0 >= m_pos(m)) ik = m;
+            const double sk = m_slope(ik);
+            const double gk0 = m_cum(ik) + ((double)k0 - m_pos(ik)) * sk;
             const double dl = (double)fa.delta;
             const double za = gk0 - (double)l0 * dl, zk = sk * (double)(nk - 1), zl = -dl * (double)(nl - 1);
             const double zlo = za + fmin(0.0, zk) + fmin(0.0, zl), zhi = za + fmax(0.0, zk) + fmax(0.0, zl);
             const double zc = 0.5 * (zlo + zhi);
             // piece A: the stripe of the tile centre; piece B: across the kink inside (zlo, zhi) that bends d* most
             int ia = 0;
-            for (int j = 1; j < WT_NB; ++j)
-                if (fabs(zc) >= __ldg(&w->gcum[j])) ia = j;
+            for (int m = 1; m < NM; ++m)
+                if (fabs(zc) >= m_cum(m)) ia = m;
             const double sgn_a = zc < 0.0 ? -1.0 : 1.0;
             int ib = ia;
-            double sgn_b = sgn_a, worst = 0.0;
+            double sgn_b = sgn_a, worst = 5.0e-5;                              // kinks that bend d* by less are ignored
             bool b_high = false;                                               // piece B lies at larger z than the centre
-            for (int j = 1; j < WT_NB; ++j) {
-                const double gb = __ldg(&w->gcum[j]);
-                const double bend = fabs(__ldg(&w->islope[j]) - __ldg(&w->islope[j - 1]));
+            for (int m = 1; m < NM; ++m) {
+                const double gb = m_cum(m);
+                const double bend = fabs(m_isl(m) - m_isl(m - 1));
                 for (int sg = 0; sg < 2; ++sg) {
                     const double zb = sg ? -gb : gb;
                     if (zb <= zlo || zb >= zhi) continue;
@@ -169,7 +190,7 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
                         worst = bend * far_side;
                         // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
                         const bool outward = sg ? (zb < zc) : (zb > zc);
-                        ib = outward ? j : j - 1;
+                        ib = outward ? m : m - 1;
                         sgn_b = sg ? -1.0 : 1.0;
                         b_high = zb > zc;
                     }
@@ -178,8 +199,8 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i
             const double inv_step = 1.0 / fa.c0_step;
             auto piece = [&](double sgn, int i, double &d_t00, double &dk, double &dll) {
-                const double isl = __ldg(&w->islope[i]);
-                d_t00 = (sgn * stripe_pos(i) + (za - sgn * __ldg(&w->gcum[i])) * isl - fa.c0_base) * inv_step - 0.5;
+                const double isl = m_isl(i);
+                d_t00 = (sgn * m_pos(i) + (za - sgn * m_cum(i)) * isl - fa.c0_base) * inv_step - 0.5;
                 dk = sk * isl * inv_step;
                 dll = -dl * isl * inv_step;
             };
@@ -200,15 +221,27 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
                 const double va = tA + ck * kA + cl * lA, vb = tB + ck * kB + cl * lB;
                 dmin = fmin(dmin, use_max ? fmax(va, vb) : fmin(va, vb));
             }
-            const int lo = (int)floor(dmin) - 1 + p.padl;  // >= 0 by construction of padl
+            // B = len * |dc/dd| at fixed line: the rays' spacing on the pixel line, i.e. their spacing at the start
+            // stretched by the warp between the start stripe and the tile's stripe
+            const double bA = (double)an.b * (m_slope(ia) / sk), bB = (double)an.b * (m_slope(ib) / sk);
+            const bool kink = !(ib == ia && sgn_b == sgn_a);
+            // rays closer than a position: a third ray can reach a pixel (weight up to len - B)
+            const bool four = fmin(bA, bB) < 0.9985 * (double)an.a0;
+            const bool mild = fabs(m_isl(ia) - m_isl(ib)) < 3.0e-4 * m_isl(ia);
+            const bool generic = four || (kink && !mild);
+            const int flags = (generic ? BP_F_GENERIC : 0) | (kink && !generic ? BP_F_KINK : 0) | (kink && !use_max ? BP_F_MIN : 0) |
+                              (four ? BP_F_FOUR : 0);
+            const int lo = (int)floor(dmin) - (four ? 2 : 1) + p.padl;  // >= 0 by construction of padl
             const int aligned = lo & ~3;
             // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
-            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2).  B = len * |dc/dd| at
-            // fixed line: the rays' spacing on the line, stretched by the warp between their start and the tile.
-            const float bw = (float)((double)an.b * (__ldg(&w->slope[ia]) / sk));
+            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
             const double off = (double)(p.padl - aligned) - 0.5;
-            sm.cst[s][lane] = make_float4((float)(vert ? kA : lA), (float)(vert ? lA : kA), (float)(tA + off), an.a0 - 0.5f * bw);
-            sm.cst2[s][lane] = make_float4((float)(vert ? kB : lB), (float)(vert ? lB : kB), (float)(tB + off), use_max ? bw : -bw);
+            sm.cst[s][lane] = make_float4((float)(vert ? kA : lA), (float)(vert ? lA : kA), (float)(tA + off), (float)((double)an.a0 - 0.5 * bA));
+            if (!kink)                           // piece B = piece A
+                sm.cst2[s][lane] = sm.cst[s][lane];
+            else
+                sm.cst2[s][lane] = make_float4((float)(vert ? kB : lB), (float)(vert ? lB : kB), (float)(tB + off), (float)((double)an.a0 - 0.5 * bB));
+            sm.cst3[s][lane] = make_float4((float)bA, (float)bB, __int_as_float(flags), 0.0f);
             src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
         }
         __syncwarp();
@@ -296,24 +329,60 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         if constexpr (POS) tap_triple_fma<V>(wa, v0, wb, v1, wc, vx, a1);
         else tap_triple_fma<V>(wa, vx, wb, v0, wc, v1, a1);
     };
-    // d* of a pixel = max or min of the angle's two affine pieces (one FMNMX with a uniform predicate)
-    auto one_angle = [&](auto pos_tag, const float4 &c4, const float4 &c5, bool use_max, float bw, const VecT *seg) {
+    // KINK: d* = max | min of two affine pieces of nearly equal slope (the lower pixel of a pair and the tap weights
+    // take piece A's slope: < 3e-4 detector off)
+    auto one_angle = [&](auto pos_tag, auto kink_tag, const float4 &c4, const float4 &c5, bool use_min, float bw, const VecT *seg) {
+        constexpr bool KINK = decltype(kink_tag)::value;
         auto dstar = [&](float j, float i) {
-            const float a = fmaf(j, c4.x, fmaf(i, c4.y, c4.z)), b = fmaf(j, c5.x, fmaf(i, c5.y, c5.z));
-            return use_max ? fmaxf(a, b) : fminf(a, b);
+            const float a = fmaf(j, c4.x, fmaf(i, c4.y, c4.z));
+            if (!KINK) return a;
+            const float b = fmaf(j, c5.x, fmaf(i, c5.y, c5.z));
+            return use_min ? fminf(a, b) : fmaxf(a, b);
         };
 #pragma unroll
         for (int j = 0; j < BP_RPT / 2; ++j) {
-            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z), dr0b = fmaf(ir[2 * j], c5.y, c5.z);
+            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z), dr0b = KINK ? fmaf(ir[2 * j], c5.y, c5.z) : 0.0f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float da = fmaf(jc[c], c4.x, dr0), db = fmaf(jc[c], c5.x, dr0b);
-                const float ds0 = use_max ? fmaxf(da, db) : fminf(da, db);
+                const float da = fmaf(jc[c], c4.x, dr0), db = KINK ? fmaf(jc[c], c5.x, dr0b) : 0.0f;
+                const float ds0 = !KINK ? da : (use_min ? fminf(da, db) : fmaxf(da, db));
                 if (2 * j + c < BpShare<V>::value) {
                     shared_pair(pos_tag, ds0, c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
                 } else {
                     single(ds0, c4, bw, seg, acc[2 * j][c]);
                     single(dstar(jc[c], ir[2 * j + 1]), c4, bw, seg, acc[2 * j + 1][c]);
+                }
+            }
+        }
+    };
+    // Generic path (BP_F_GENERIC): d* = max or min of the two affine pieces, each pixel located on its own with the tap
+    // spacing of the piece it falls on; with BP_F_FOUR the two outer candidates idx - 1 and idx + 2 get their weights
+    // max(0, len - B * distance) too (they vanish unless the rays are closer than a position).
+    auto one_angle_generic = [&](const float4 &c4, const float4 &c5, const float4 &c6, const VecT *seg) {
+        const int flags = __float_as_int(c6.z);
+        const bool use_min = (flags & BP_F_MIN) != 0, four = (flags & BP_F_FOUR) != 0;
+#pragma unroll
+        for (int r = 0; r < BP_RPT; ++r) {
+            const float dra = fmaf(ir[r], c4.y, c4.z), drb = fmaf(ir[r], c5.y, c5.z);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float da = fmaf(jc[c], c4.x, dra), db = fmaf(jc[c], c5.x, drb);
+                const bool on_b = use_min ? (db < da) : (db > da);
+                const float ds = on_b ? db : da, bw = on_b ? c6.y : c6.x, ah = on_b ? c5.w : c4.w;
+                int idx;
+                float f;
+                locate(ds, idx, f);
+                idx = min(max(idx, 1), BP_SEGW - 3);       // a tile whose shadow outgrows the segment (rays compressed by > 10 %)
+                const float w0 = fmaxf(0.0f, fmaf(-bw, f, ah)), w1 = fmaxf(0.0f, fmaf(bw, f, ah));
+                float v0[V], v1[V];
+                unpack<V>(seg[idx], v0);
+                unpack<V>(seg[idx + 1], v1);
+                tap_pair_fma<V>(w0, v0, w1, v1, acc[r][c]);
+                if (four) {
+                    const float wm = fmaxf(0.0f, fmaf(-bw, f, ah - bw)), wp = fmaxf(0.0f, fmaf(bw, f, ah - bw));
+                    unpack<V>(seg[idx - 1], v0);
+                    unpack<V>(seg[idx + 2], v1);
+                    tap_pair_fma<V>(wm, v0, wp, v1, acc[r][c]);
                 }
             }
         }
@@ -324,12 +393,19 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
-            const float4 c4 = sm.cst[s][k], c5 = sm.cst2[s][k];
-            const float bw = fabsf(c5.w);
-            const bool use_max = c5.w >= 0.0f;
+            const float4 c4 = sm.cst[s][k], c6 = sm.cst3[s][k];
             const VecT *seg = &sm.seg[s][k][0];
-            if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), c4, c5, use_max, bw, seg);
-            else one_angle(std::false_type(), c4, c5, use_max, bw, seg);
+            const int flags = __float_as_int(c6.z);
+            if (flags & BP_F_GENERIC) one_angle_generic(c4, sm.cst2[s][k], c6, seg);
+            else if (flags & BP_F_KINK) {
+                const float4 c5 = sm.cst2[s][k];
+                const bool use_min = (flags & BP_F_MIN) != 0;
+                if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), std::true_type(), c4, c5, use_min, c6.x, seg);
+                else one_angle(std::false_type(), std::true_type(), c4, c5, use_min, c6.x, seg);
+            } else {
+                if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), std::false_type(), c4, c4, false, c6.x, seg);
+                else one_angle(std::false_type(), std::false_type(), c4, c4, false, c6.x, seg);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s

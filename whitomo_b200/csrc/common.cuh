@@ -70,7 +70,7 @@ struct BpAngle {
 // oracle/astra_linear.c:93,120).  While |c| stays inside one binade [2^e, 2^(e+1)) every addition rounds to that
 // binade's grid u = 2^(e-23), so the ray does not advance by delta but by step_e = rint(delta / u) * u: its speed
 // depends on WHERE it is, not on which ray it is.  Integrating dc/dl = step(|c|) gives the "unwarped" coordinate
-//     G(c) = int_0^c delta / step(|c'|) dc'      (odd, piecewise linear, slope 1 for |c| < 64, kinks at +-2^e)
+//     G(c) = int_0^c delta / step(|c'|) dc'      (odd, piecewise linear, slope 1 for |c| < 4, kinks at +-2^e)
 // in which every ray moves at the nominal speed again:  G(c_l) = G(c_0) + l * delta.  The reference's position is
 // therefore  c_l(d) = Ginv(G(c_0(d)) + l * delta)  up to the O(u) discretisation at the <= 12 binade crossings of a
 // ray (measured: 1.5e-4 pixel rms at N = 2048 and 3e-4 at N = 8192, where the plain closed form c_0 + l * delta is
@@ -78,17 +78,18 @@ struct BpAngle {
 // staging windows and line ranges (its positions themselves repeat the float32 sum literally); K2 inverts the map:
 // the detector coordinate of pixel (line l, position k) is  d* = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
 // Under WT_POS_EXACT every slope is 1 and G is the identity.
-constexpr int WT_NB = 11;   // stripes of |position|: [0, 64), [64, 128), ..., [2^15, inf)
+constexpr int WT_NB = 15;   // stripes of |position|: [0, 4), [4, 8), ..., [2^15, inf)
+constexpr double WT_STUCK_SLOPE = 1048576.0;   // slope of G where the reference's ray does not move at all (|delta| < u/2)
 struct WarpAngle {
     double gcum[WT_NB];     // G at the lower edge of stripe i (gcum[0] = 0)
     double slope[WT_NB];    // dG/dc inside stripe i = delta / step_i
     double islope[WT_NB];   // 1 / slope
 };
-__host__ __device__ inline double stripe_pos(int i) { return i == 0 ? 0.0 : (double)(32 << i); }
+__host__ __device__ inline double stripe_pos(int i) { return i == 0 ? 0.0 : (double)(2 << i); }
 __host__ __device__ inline int stripe_of(double a) {   // a >= 0
     int i = 0;
     for (int j = 1; j < WT_NB; ++j)
-        if (a >= (double)(32 << j)) i = j;
+        if (a >= (double)(2 << j)) i = j;
     return i;
 }
 __host__ __device__ inline double warp_g(const WarpAngle &w, double c) {

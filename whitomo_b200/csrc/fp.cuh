@@ -203,8 +203,8 @@ __device__ __forceinline__ float warp_g_f(const float *gcum, const float *islope
     int i = 0;
 #pragma unroll
     for (int j = 1; j < WT_NB; ++j)
-        if (a >= (float)(32 << j)) i = j;
-    const float pos = i ? (float)(32 << i) : 0.0f;
+        if (a >= (float)(2 << j)) i = j;
+    const float pos = i ? (float)(2 << i) : 0.0f;
     return copysignf(gcum[i] + __fdividef(a - pos, islope[i]), c);
 }
 __device__ __forceinline__ float warp_ginv_f(const float *gcum, const float *islope, float z) {
@@ -213,7 +213,7 @@ __device__ __forceinline__ float warp_ginv_f(const float *gcum, const float *isl
 #pragma unroll
     for (int j = 1; j < WT_NB; ++j)
         if (a >= gcum[j]) i = j;
-    const float pos = i ? (float)(32 << i) : 0.0f;
+    const float pos = i ? (float)(2 << i) : 0.0f;
     return copysignf(fmaf(a - gcum[i], islope[i], pos), z);
 }
 
@@ -305,8 +305,9 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         } else {
             const float inv = 1.0f / delta;
             const float t0 = (-1.05f - z0) * inv, t1 = (zn + 0.05f - z0) * inv;
-            l_lo = (int)fmaxf(floorf(fminf(t0, t1)), 0.0f);
-            l_hi = (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)nlines);
+            // (a ray that starts where the reference's sum does not move has |z0| ~ 1e10: clamp before converting)
+            l_lo = (int)fminf(fmaxf(floorf(fminf(t0, t1)), 0.0f), (float)nlines);
+            l_hi = (int)fminf(fmaxf(ceilf(fmaxf(t0, t1)) + 1.0f, 0.0f), (float)nlines);
         }
         // chunk boundaries come from ALL rays of the tile, so that a ray's rounding sequence (and result bits)
         // does not depend on which angle range a call asks for
