@@ -114,15 +114,17 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------------------
 def cpu_grad_sample(n_angles_sample, threads):
     """One func+grad evaluation of the reference's white-beam model (src/white_projection.py:86-127: K FP,
-    numpy float64 point-wise work over (rays, E), K BP) on ONE 2048^2 slice restricted to every
-    (1800 // n_angles_sample)-th angle of the C4 geometry.  Returns (seconds, updates)."""
+    numpy float64 point-wise work over (rays, E), K BP) on ONE 2048^2 slice; n_angles_sample = 1800 is the C4
+    configuration itself, fewer angles take every (1800 // n)-th angle of it.  Returns (seconds, updates)."""
     import oracle
     from oracle import white as ow
     from whitomo_b200 import phantoms
     grid, source, ea, pix = phantoms.synth_spectrum(E, N)
     angles = np.linspace(0, np.pi, A)[:: max(1, A // n_angles_sample)][:n_angles_sample]
     geom = oracle.Geometry(N, N, D, angles)
-    wo = ow.WhiteOracle(source, pix, ea, grid, (N, N), geometry=geom)
+    # the reference's arithmetic ray by ray, with its (rays, E) float64 temporaries built 256k rays at a time
+    # (unchunked they are 5.3 + 3 x 2.7 GB at all 1800 angles); bit-identical results (tests/test_oracle_golden.py)
+    wo = ow.ChunkedWhiteOracle(source, pix, ea, grid, (N, N), geometry=geom)
     wo.FP = lambda x: oracle.fp(geom, x, threads=threads)
     wo.BP = lambda x: oracle.bp(geom, x, threads=threads)
     gt = phantoms.two_discs(N)
@@ -142,22 +144,22 @@ def cpu_baseline_block(budget_s=20.0):
     n_s = int(max(8, min(A, 8 * budget_s / max(dt, 1e-3))))
     n_s = min(n_s, 225)
     dt, upd = cpu_grad_sample(n_s, 1)
-    return {"value": upd / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": upd / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "angles": n_s,
             "sample": "one func+grad (K=2 FP + K=2 BP + numpy white-beam model, E=64) on one 2048^2 slice, "
                       "%d of the 1800 angles, single thread, %.1f s" % (n_s, dt)}
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on the SAME configuration: every step is one func+grad of the
+    white-beam model on one 2048^2 slice at ALL 1800 angles (about 20 s on 16 host threads), the oracle port on all
+    host threads.  WT_BENCH_REF_ANGLES (tests only) shrinks the angle set."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     oracle.build()
     threads = oracle.num_threads()
-    probe = max(32, 2 * threads)
-    dt, _ = cpu_grad_sample(probe, threads)               # probe, also warms the page cache
-    target_s = float(os.environ.get("WT_BENCH_REF_SECONDS", "6"))         # CPU seconds per step (tests shrink it)
-    n_s = int(max(probe, min(A, probe * target_s / max(dt, 1e-3))))
+    n_s = int(os.environ.get("WT_BENCH_REF_ANGLES", str(A)))
     for _ in range(min(args.warmup, 1)):
         cpu_grad_sample(n_s, threads)
     times, upd = [], 0.0
@@ -166,14 +168,15 @@ def run_reference(args):
         times.append(dt)
     t = float(np.mean(times))
     val = upd / t / 1e9
-    sample = ("one func+grad per step on one 2048^2 slice, %d of the 1800 angles, %d host threads (pthreads over "
+    sample = ("one func+grad per step on one 2048^2 slice, %s angles, %d host threads (pthreads over "
               "angles), numpy float64 white-beam model; the reference's loop spends 3K FP + K BP per iteration, "
-              "only K FP + K BP are counted here" % (n_s, threads))
+              "only K FP + K BP are counted here" % ("all 1800" if n_s == A else "%d of the 1800" % n_s, threads))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "slices_per_step": 1, "angles": n_s, "sample": sample,
+                   "warmup_steps_run": min(args.warmup, 1)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "barrier_iters_per_s": 1.0 / t * (n_s / float(A)),
@@ -183,6 +186,79 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # GPU side
 # --------------------------------------------------------------------------------------------------
+def c5_angle_split(dev, rank, world, positions, reps=5):
+    """BASELINE configs[4]: ONE 8192^2 slice, 4096 angles, split by angle range over the ranks -- the only data-path
+    collective of the project (whitomo_b200/distributed.py: AngleSplit).  One iteration = FP of the rank's angle range,
+    partial backprojection of those rows row block by row block, all-reduce of the finished blocks over NCCL while the
+    next block is computed.  Timed with CUDA events, max over ranks; rank 0 also times the same iteration alone on its
+    GPU (all angles) for the speed-up, and checks the distributed W^T against the single-GPU one."""
+    import torch
+    import torch.distributed as dist
+    from whitomo_b200.projector import Projector
+    from whitomo_b200.distributed import AngleSplit
+    n, na = 8192, 4096
+    d = int(np.sqrt(2) * n + 1)
+    P = Projector(n, n, d, np.linspace(0, np.pi, na), device=dev, positions=positions)
+    sp = AngleSplit(P)
+    gen = torch.Generator(device=dev).manual_seed(5)           # same data on every rank
+    x = torch.rand((n, n), device=dev, generator=gen)
+    y = torch.rand((na, d), device=dev, generator=gen)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n_rep):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(n_rep):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n_rep
+
+    def iteration():
+        return sp.bp(sp.fp(x))
+
+    iteration()
+    t_split = timed(iteration, reps)
+    r_loc = sp.fp(x)
+    part = P.bp(r_loc, angle_range=sp.range)
+    parts = [timed(lambda: sp.fp(x), 3), timed(lambda: P.bp(r_loc, angle_range=sp.range), 3),
+             timed(lambda: sp._allreduce(part), 3)]
+    tt = torch.tensor([t_split] + parts, device=dev, dtype=torch.float64)
+    allt = [torch.zeros_like(tt) for _ in range(world)]
+    dist.all_gather(allt, tt)
+    dbp = sp.bp(y)
+    out = None
+    if rank == 0:
+        full = P.bp(y)
+        err = float(torch.linalg.vector_norm((dbp - full).double()) / torch.linalg.vector_norm(full.double()))
+        del full
+        a, b = ev(), ev()
+        P.bp(P.fp(x))
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(2):
+            P.bp(P.fp(x))
+        b.record()
+        torch.cuda.synchronize()
+        t1 = a.elapsed_time(b) / 2
+        t_max = max(float(v[0]) for v in allt)
+        out = {"positions": positions, "ms_per_iteration": t_max, "ms_per_iteration_single_gpu": t1,
+               "speedup_vs_single_gpu": t1 / t_max, "efficiency": t1 / t_max / world,
+               "gups": 2.0 * n * n * na / (t_max * 1e-3) / 1e9,
+               "bp_rel_l2_vs_single_gpu": err,
+               "per_rank_ms": {"fp": [round(float(v[1]), 3) for v in allt], "bp_local": [round(float(v[2]), 3) for v in allt],
+                               "allreduce_alone": [round(float(v[3]), 3) for v in allt]},
+               "angle_ranges": [list(r) for r in sp.ranges], "bp_row_blocks": sp.bp_blocks}
+    dist.barrier()
+    del P, sp, x, y, dbp, part, r_loc
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -325,6 +401,14 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_elapsed = float(tt.item())
 
+    # ---- the collective path (BASELINE configs[4]) rides along whenever there is more than one rank ----------
+    c5 = None
+    if world > 1 and not args.no_c5:
+        del h_x, h_meas, h_out, xd, md
+        c5 = {"config": "C5: one 8192x8192 slice, 4096 angles, D=11586, split by angle range over %d ranks; FP rows local, "
+                        "partial BP summed by NCCL all-reduce, row block by row block behind the backprojection" % world,
+              "runs": [c5_angle_split(dev, rank, world, mode) for mode in ("astra", "exact")]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,8 +454,8 @@ def run_gpu(args):
         "roofline": None, "roofline_other": None,
         "roofline_update": dict(roof(up_bytes, t_up, "update"), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3)"),
         "e2e": {"value": upd_per_step * args.steps / e2e_elapsed / 1e9, "unit": UNIT,
-                "h2d_bytes_per_step": int(h_x.numel() * 4 + h_meas.numel() * 4) * world,
-                "d2h_bytes_per_step": int(h_out.numel() * 4 + h_loss.numel() * 8) * world,
+                "h2d_bytes_per_step": int(S * K * N * N * 4 + S * A * D * 4) * world,
+                "d2h_bytes_per_step": int(S * K * N * N * 4 + S * 8) * world,
                 "ms_per_step": e2e_elapsed / args.steps * 1e3,
                 "what": "every step: pinned host concentrations + measured sinograms -> device, one barrier iteration "
                         "through Projector.white_fp/bp/barrier_update, updated concentrations + loss -> pinned host; "
@@ -380,7 +464,10 @@ def run_gpu(args):
         "gpu_launches": 7 * args.steps,   # per step: pack_vol, fp, reduce, pack_sino, bp, barrier_update, reduce
         "clocks": clocks,
         "loss_after": final_loss,
+        "positions": proj.positions,
     }
+    if c5 is not None:
+        out["c5_angle_split"] = c5
     tot = t_fp + t_bp + t_up
     note = ("gather/stencil kernel with ~N-fold on-chip reuse: bound by shared-memory load bandwidth (see `onchip`), "
             "not HBM (SURVEY 8d: compulsory-bytes ceiling of the HBM fraction is ~0.4%)")
@@ -408,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slices", type=int, default=8, help="resident slices per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the 8192^2 angle-split record")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout
     # when NCCL_DEBUG is set), so file descriptor 1 points at stderr while the benchmark runs and the JSON line goes

@@ -89,6 +89,18 @@ int wt_fp(const wt_geom *g, const float *vol, float *sino, int nimages, int angl
 int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end,
           float scale, void *ws, size_t ws_bytes, void *stream);
 
+/* The same operator, row block by row block: only rows [row_begin, row_end) of the rows the backprojector assigns a
+ * thread to are computed and written (row_end < 0: through the last one), so that a caller can hand finished blocks to
+ * a collective while later blocks are still being computed (the angle-range split of one oversized slice sums the
+ * ranks' partial backprojections: whitomo_b200/distributed.py).  wt_bp_row_info tells how many rows are processed
+ * (all `rows`; under WT_POS_EXACT with one or two large images only the upper half, rows [0, ceil(rows/2)), and a
+ * block then also writes its point reflection, rows [rows - row_end, rows - row_begin)), the alignment row_begin must
+ * have, and whether blocks are mirrored.  reuse_packed != 0: `ws` still holds the packed sinogram of a previous call
+ * with the same sino / nimages / angle range (skips the re-pack). */
+int wt_bp_rows(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end,
+               int row_begin, int row_end, int reuse_packed, float scale, void *ws, size_t ws_bytes, void *stream);
+int wt_bp_row_info(const wt_geom *g, int nimages, int *rows_processed, int *row_align, int *mirrored);
+
 /* x = SIRT(p, n_iters), x0 = 0.  Replaces cpu_sirt (src/astra_proxy.py:69-84: ASTRA 'SIRT').
  * sino (nimages, nangles, ndet) -> vol (nimages, rows, cols). */
 int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_iters, void *ws,

@@ -51,8 +51,9 @@ class BarrierFunction(object):
 def barrier_method(x0, goal_function, reg_dict=None, ineq_dict=None, n_iter=200, t0=1.0, n_biter=10,
                    alpha=0.1, beta_reg=1.0, t_step=0.1, add_stat_cb=None, max_iter=1000,
                    do_alpha_decay=True, min_delta_loss=1e-3, n_steps_without_progress=None,
-                   trace=None):
-    """src/barrier_method.py:79-240.  ``trace`` (a list) receives the loss of every early-stop check."""
+                   trace=None, on_iter=None):
+    """src/barrier_method.py:79-240.  ``trace`` (a list) receives the loss of every early-stop check;
+    ``on_iter(i_biter, i_iter, x)`` (test instrumentation, not in the reference) sees every iterate."""
     reg_dict = reg_dict or {}
     ineq_dict = ineq_dict or {}
     objs, bf = {}, {}
@@ -67,9 +68,9 @@ def barrier_method(x0, goal_function, reg_dict=None, ineq_dict=None, n_iter=200,
         if not all(v.is_feasible(x0) for v in objs.values()):
             return x0, None
     t, x = t0, x0
-    for _ in range(n_biter):                                            # :159
+    for i_biter in range(n_biter):                                      # :159
         prev_loss, stall = None, 0
-        for _ in range(n_iter):                                         # :163
+        for i_iter in range(n_iter):                                    # :163
             grad = goal_function[1](x)
             reg_grads = [v[1](x) for v in reg_dict.values()]
             bf_grads = [v[1](x) for v in bf.values()]
@@ -82,6 +83,8 @@ def barrier_method(x0, goal_function, reg_dict=None, ineq_dict=None, n_iter=200,
             x = x + (-alpha * grad)                                     # :176,201
             for v in objs.values():                                     # :205-206
                 x = v.project(x)
+            if on_iter is not None:
+                on_iter(i_biter, i_iter, x)
             if n_steps_without_progress is not None:                    # :208-229
                 loss = goal_function[0](x)
                 for v in reg_dict.values():
@@ -157,7 +160,8 @@ def ray_transform_from_projection(p, bound, i0):
 
 
 def barrier_least_squares(FP, BP, v_shape, pr, i0, bound, n_iter=200, n_biter=10, t0=0.2, t_step=0.2,
-                          alpha=0.1, max_iter=400, with_sino_barrier=True, do_alpha_decay=False, trace=None):
+                          alpha=0.1, max_iter=400, with_sino_barrier=True, do_alpha_decay=False, trace=None,
+                          on_iter=None):
     """First run of teeth_recon/experiments.py:651-749 with FP/BP injected (flat in, flat out).
 
     cost = sum(((FPx-b)[~m]/n_good)^2); grad = 2 BP((FPx-b)[~m]/n_good)  (B8: not the true gradient; kept).
@@ -190,5 +194,5 @@ def barrier_least_squares(FP, BP, v_shape, pr, i0, bound, n_iter=200, n_biter=10
     x0 = 1e-2 + np.zeros(v_shape, dtype="float32").flatten()
     ans, _ = barrier_method(x0, (cost, grad), ineq_dict=ineq, n_iter=n_iter, n_biter=n_biter, t0=t0,
                             t_step=t_step, beta_reg=1.0, alpha=alpha, max_iter=max_iter,
-                            do_alpha_decay=do_alpha_decay, trace=trace)
+                            do_alpha_decay=do_alpha_decay, trace=trace, on_iter=on_iter)
     return ans.reshape(v_shape)

@@ -84,6 +84,48 @@ class WhiteOracle(object):
         return self.BP_white(q, exp)[0]
 
 
+class ChunkedWhiteOracle(WhiteOracle):
+    """Same arithmetic as WhiteOracle, ray by ray, with the (rays, E) float64 temporaries of FP_white / calc_mu built
+    for `chunk` rays at a time (at 2048^2 x 1800 x 64 bins the reference's temporaries are 5.3 + 3 x 2.7 GB).  Every
+    operation is element-wise or a sum along E of one ray, so func and grad are bit-identical to the unchunked class
+    (tests/test_oracle_golden.py checks that)."""
+
+    chunk = 1 << 18
+
+    def _model(self, c, want_mu):
+        K = len(c)
+        conc_fp = np.array([self.FP(cc) for cc in c]).reshape(K, -1)
+        R = conc_fp.shape[1]
+        integral = np.empty(R)
+        mu = np.empty((K, R)) if want_mu else None
+        ea = self.element_absorptions.reshape(K, 1, -1)
+        src = self.source.reshape(1, -1)
+        for r0 in range(0, R, self.chunk):
+            r1 = min(R, r0 + self.chunk)
+            flat_fp = conc_fp[:, r0:r1].reshape(K, -1, 1)
+            exp = np.exp(-self.pixel_size * np.sum(flat_fp * ea, axis=0))
+            integral[r0:r1] = integrate(src * exp, self.energy_grid)
+            if want_mu:
+                for k, eak in enumerate(self.element_absorptions):
+                    mu[k, r0:r1] = -integrate(src * self.pixel_size * exp * eak.reshape(1, -1), self.energy_grid)
+        return integral, mu
+
+    def calc_sinogram_with_gt(self, gt):
+        self.sinogram = self._model(gt, False)[0]
+
+    def func(self, c):
+        q = self.sinogram - self._model(c, False)[0]
+        return 0.5 * np.linalg.norm(q) ** 2
+
+    def grad(self, c):
+        fp, mu = self._model(c, True)
+        bp_arg = (self.sinogram - fp) * mu
+        conc = np.zeros(self.conc_shape, dtype=np.float64)
+        for k in range(conc.shape[0]):
+            conc[k] = -self.BP(bp_arg[k].reshape(self.proj_shape))
+        return conc
+
+
 def calc_uneq_reg_grad(c):
     """d|c0 c1|/dc_i = sum_{j != i} c_j * sign(c0 c1)  (src/white_rec.py:180-186)."""
     out = np.zeros_like(c)

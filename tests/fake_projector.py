@@ -36,6 +36,17 @@ class OracleProjector(object):
                 out[i] = scale * oracle.bp(g, s[i, a0:a1])
         return torch.from_numpy(out.reshape(tuple(sino.shape[:-2]) + self.vol_shape))
 
+    def bp_row_blocks(self, nimages, nblocks):
+        """same contract as Projector.bp_row_blocks (no mirror pairing, tile height 4)"""
+        per = -(-self.rows // max(1, nblocks))
+        per = -(-per // 4) * 4
+        return [(b0, min(self.rows, b0 + per), [(b0, min(self.rows, b0 + per))]) for b0 in range(0, self.rows, per)]
+
+    def bp_rows(self, sino, out, row_begin, row_end, angle_range=None, scale=1.0, reuse_packed=False):
+        full = self.bp(sino, angle_range=angle_range, scale=scale).reshape(out.shape)
+        out[:, row_begin:row_end] = full[:, row_begin:row_end]
+        return out
+
     def white_fp(self, spectrum, conc, meas=None, want_intensity=True, want_qmu=True, want_loss=True, angle_range=None):
         """spectrum: an oracle.white.WhiteOracle carrying the tables"""
         c = conc.numpy().astype(np.float64)

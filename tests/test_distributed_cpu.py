@@ -41,7 +41,9 @@ def _worker(rank, world, port, out):
         loc = sp.fp(x)
         ok = bool(torch.equal(loc[a0:a1], full_fp[a0:a1])) and float(loc[:a0].abs().sum() + loc[a1:].abs().sum()) == 0.0
         ok = ok and rel_l2(sp.gather_sinogram(loc).numpy(), full_fp.numpy()) < 1e-7
-        ok = ok and rel_l2(sp.bp(y, scale=-1.0).numpy(), -full_bp.numpy()) < 1e-6
+        ok = ok and rel_l2(sp.bp(y, scale=-1.0).numpy(), -full_bp.numpy()) < 1e-6      # row blocks + async all-reduces
+        one = AngleSplit(P, bp_blocks=1)                                                 # one backprojection, one all-reduce
+        ok = ok and rel_l2(one.bp(y, scale=-1.0).numpy(), -full_bp.numpy()) < 1e-6
         # white-beam func/grad split by angle == unsplit
         E = 4
         grid = np.stack([np.linspace(1, 9, E), rng.uniform(0.5, 1.5, E)]).T
@@ -85,3 +87,28 @@ def test_range_helpers():
         r = angle_ranges(n, w)
         assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
     assert all(a % 8 == 0 for a, _ in angle_ranges(1800, 8))
+
+
+def test_cost_balanced_angle_ranges():
+    """cuts fall on tile boundaries, cover the angle list, and give the ranks around 45 degrees (small tiles: the
+    forward projector pays per tile) fewer angles"""
+    from whitomo_b200.distributed import angle_ranges_by_cost
+    first, count = [], []
+    a = 0
+    for t in range(64):                      # 8-angle tiles, except a band of 4-angle tiles in the middle
+        c = 4 if 24 <= t < 40 else 8
+        first.append(a)
+        count.append(c)
+        a += c
+    r = angle_ranges_by_cost(first, count, a, 4)
+    assert r[0][0] == 0 and r[-1][1] == a and all(r[i][1] == r[i + 1][0] for i in range(3))
+    assert all(lo in first or lo == a for lo, _ in r)
+    cost = lambda lo, hi: sum(0.55 * 8 + 0.45 * c for f, c in zip(first, count) if lo <= f < hi)
+    costs = [cost(*x) for x in r]
+    assert max(costs) - min(costs) <= 2 * 8                     # within two tiles of each other
+    assert (r[1][1] - r[1][0]) < (r[0][1] - r[0][0])            # the band of small tiles gets fewer angles
+    # equal tiles: equal counts
+    assert angle_ranges_by_cost(list(range(0, 64, 8)), [8] * 8, 64, 4) == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    # more ranks than tiles: trailing ranks get empty ranges, nothing is lost
+    r = angle_ranges_by_cost([0, 8], [8, 8], 16, 4)
+    assert r[0][0] == 0 and r[-1][1] == 16 and sum(hi - lo for lo, hi in r) == 16

@@ -34,37 +34,52 @@ def test_c1_mono_fp_bp_and_100_sirt_iterations(golden):
     assert rel_l2(rec, ph) < 0.3
 
 
-def test_c2_white_rec_512(golden):
-    """configs[1]: 512x512, 360 angles, 64-bin spectrum, white_rec gradient reconstruction (200 iterations on the
-    device; the first 4 iterations are compared with the oracle's restatement of Iteration)"""
-    from whitomo_b200 import phantoms, solvers
-    from whitomo_b200.projector import Projector, Spectrum
-    n, na = 512, 360
-    grid, source, ea, pix = phantoms.synth_spectrum(64, n)
-    wo = ow.WhiteOracle(source, pix, ea, grid, (n, n), n_angles=na)
-    wo.FP = lambda x: oracle.fp(wo.geom, x, threads=0)          # all host threads: same arithmetic per ray
-    gt = phantoms.two_discs(n).astype(np.float64)
-    wo.calc_sinogram_with_gt(gt)
-    P = Projector(n, n, wo.geom.ndet, np.linspace(0, np.pi, na))
-    sp = Spectrum(wo.source, grid[:, 1], ea, pix)
-    meas = P.white_fp(sp, torch.from_numpy(gt.astype(np.float32)).cuda(), want_qmu=False, want_loss=False)[0]
-    assert rel_l2(meas.cpu().numpy().ravel(), wo.sinogram) < 1e-4
-    rng = np.random.default_rng(12345)
-    c0 = (0.1 + rng.uniform(-0.01, 0.01, gt.shape)).astype(np.float32)
-    c = c0.astype(np.float64)
-    for it in range(4):
-        c, _ = ow.iteration(wo, c, 0.7, 1e-2, clip_concentrations=True, dissimilarity_constraint=True,
-                            triv_conc_constraint=True, iter_num=it)
-    cd, _ = solvers.white_rec_stack(P, sp, meas, torch.from_numpy(c0).cuda(), n_iters=4)
-    assert rel_l2(cd[0].cpu().numpy(), c) < 1e-3
-    cd, losses = solvers.white_rec_stack(P, sp, meas, torch.from_numpy(c0).cuda(), n_iters=200)
-    l = [x.item() for x in losses]
-    assert np.isfinite(l).all() and l[-1] < 0.5 * l[0]
-    assert 0.0 <= cd.min().item() and cd.max().item() <= 1.0
+def _scenarios():
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("parity_scenarios", os.path.join(ROOT, "tools", "parity_scenarios.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
-def test_c3_metal_artifact_reduction_1024():
-    """configs[2]: 1024x1024 teeth-like phantom with a metal insert, 720 angles, log-barrier MAR"""
+def test_c2_white_rec_512_all_200_iterations_vs_oracle():
+    """configs[1]: 512x512, 360 angles, 64-bin spectrum, white_rec gradient reconstruction: ALL 200 `Iteration`s
+    (src/white_rec.py:199-244, alpha 0.7, beta 1e-2, clip + dissimilarity + trivial-concentration terms, element
+    alternation) on the device against the oracle's restatement, iterate by iterate (measured: 2.5e-7 after one
+    iteration, 4.9e-6 after 200; profiles/r2_parity_scenarios.json)"""
+    res = _scenarios().scenario_c2(200)
+    assert [r["iteration"] for r in res["iterates"]][-1] == 200
+    for r in res["iterates"]:
+        assert r["rel_l2"] < 1e-3, r
+        assert abs(r["loss_gpu"] - r["loss_oracle_prev_iterate"]) < 1e-4 * r["loss_oracle_prev_iterate"], r
+    assert res["iterates"][-1]["rel_l2"] < 1e-4                        # two orders inside north_star's 1e-3
+    assert res["iterates"][-1]["loss_gpu"] < 0.5 * res["iterates"][0]["loss_gpu"]
+
+
+def test_c3_metal_artifact_reduction_1024_reference_parameters():
+    """configs[2]: 1024x1024 tooth phantom with a gold insert, 720 angles, barrier_least_squares with the reference's
+    OWN parameters (teeth_recon/experiments.py:737-749: n_iter 200, n_biter 10, t0 0.2, t_step 0.2, alpha 0.1).  Those
+    step sizes are tuned to the reference's 64^2 run: at 1024^2 its feasibility projection lifts the image to 1.5..46,
+    five steps walk the minimum down to 0.147, the sixth clips 3004 pixels to exactly 0, the seventh barrier gradient
+    is -1/0 and the eighth iterate is NaN everywhere -- in the reference's arithmetic (oracle) and on the device alike.
+    Parity is asserted on every iterate the reference itself keeps finite (measured 3.6e-6 .. 4.4e-6)."""
+    res = _scenarios().scenario_c3(9)
+    it = res["iterates"]
+    for r in it[:6]:
+        assert r["oracle"]["nan"] == 0 and r["oracle"]["inf"] == 0
+        assert r["same_nonfinite_pixels"] and r["rel_l2_on_finite_pixels"] < 1e-3, r
+    assert it[4]["oracle"]["zeros"] == 0 and it[5]["oracle"]["zeros"] > 0           # the sixth step reaches x = 0 ...
+    assert abs(it[5]["gpu"]["zeros"] - it[5]["oracle"]["zeros"]) <= 4               # ... on the same pixels (+- rounding)
+    assert it[6]["oracle"]["inf"] > 0 and abs(it[6]["gpu"]["inf"] - it[6]["oracle"]["inf"]) <= 4   # -1/0 on both sides
+    assert it[7]["oracle"]["nan"] == 1024 * 1024                                    # the reference's own breakdown ...
+    assert it[7]["gpu"]["nan"] + it[7]["gpu"]["inf"] > 0.9 * 1024 * 1024            # ... and the device does not hide it
+
+
+def test_c3_metal_artifact_reduction_1024_scaled_steps():
+    """the same scenario with step sizes that do work at 1024^2 (30x smaller alpha, two barrier levels): what the method
+    promises -- a finite, non-negative image satisfying the sinogram-domain barrier, data term falling per level"""
     from whitomo_b200 import phantoms, solvers, synthesis
     from whitomo_b200.projector import Projector
     n, na = 1024, 720
@@ -76,13 +91,6 @@ def test_c3_metal_artifact_reduction_1024():
     counts = synthesis.create_projection_with_poisson_noise(i0, P, ph, generator=gen)
     starved = (counts <= bound).float().mean().item()
     assert 0.0 < starved < 0.2                                   # the gold insert starves a fraction of the rays
-    # The reference hard-codes its step sizes for its own 64x64 / 90-angle run (teeth_recon/experiments.py:887-889,
-    # 741-749; projection step 1e-2 at teeth_recon/barrier.py:30).  Neither scales with N*A: at 1024^2 the feasibility
-    # projection overshoots by ~40x and alpha = 0.1 walks pixels across x = 0, after which the barrier term is -1/0
-    # (the same failure the reference's own schedule reaches at 32^2 after 8 outer iterations, see make_golden.py).
-    # The scenario is therefore run with a 30x smaller step and two barrier levels; what is checked is what the
-    # method promises: a finite, non-negative image that satisfies the sinogram-domain barrier, with the data term
-    # going down at every barrier level.
     costs = []
     x = solvers.barrier_least_squares(P, counts, i0, bound, n_iter=200, n_biter=2, alpha=0.003,
                                       on_outer=lambda d: costs.append(d["stats"][0, 0].item()))
@@ -90,3 +98,14 @@ def test_c3_metal_artifact_reduction_1024():
     assert len(costs) == 2 and costs[1] < costs[0]
     m = counts <= bound
     assert (P.fp(x)[m] >= 0.95 * np.log(i0 / bound) - 1e-3).all()
+
+
+def test_c4_gogo_barrier_iterations_one_slice_vs_oracle():
+    """configs[3], one slice: the first 3 inner iterations of the white-beam log-barrier run with the gogo parameters
+    (src/barrier_method_gogo.py:179-193: alpha 1, t0 0.1, beta 1, 0.05 |c0 c1|) at 2048^2 x 1800 x E=64 against the
+    oracle's barrier_method over its (chunked) white-beam model; 10 iterations are in profiles/r2_parity_scenarios.json
+    (1.5e-7 .. 6.9e-4: alpha = 1 is bang-bang at this size and a pixel or two land on the other face of the box)"""
+    res = _scenarios().scenario_c4(3)
+    for r in res["iterates"]:
+        assert r["rel_l2"] < 1e-3, r
+    assert res["iterates"][0]["rel_l2"] < 1e-5

@@ -25,6 +25,9 @@ SIGNATURES = {
     "wt_mar_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                           c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "wt_bp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "wt_bp_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t,
+                           c_void_p]),
+    "wt_bp_row_info": (c_int, [c_void_p, c_int] + [ctypes.POINTER(c_int)] * 3),
     "wt_sirt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "wt_sirt_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "wt_spectrum_create": (c_int, [c_int, c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_double),

@@ -121,9 +121,11 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     return fp_blocks(g);
 }
 
+// rows [row_begin, row_end) of the rows that get a thread (all rows, or the upper half under mirror pairing, where the
+// point-reflected rows are written too); row_end < 0: all of them.  packed: `sp` already holds the packed sinogram.
 template <class Epi>
 static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
-                  cudaStream_t st) {
+                  cudaStream_t st, int row_begin = 0, int row_end = -1, bool packed = false) {
     BpParams p;
     p.sp = sp; p.ang = g->d_bp; p.fang = g->d_fp; p.warp = g->d_warp;
     p.R = g->rows; p.C = g->cols; p.A = g->nangles;
@@ -131,19 +133,24 @@ static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a
     p.a_begin = a_begin; p.a_end = a_end;
     p.nimg = n;
     const Epi epi = epi_proto;
-    if (use_mirror(g, n)) {
-        p.Rproc = (g->rows + 1) / 2;
-        if (n == 1) { launch_pack_sino<2, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
-        else { launch_pack_sino<4, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
+    const bool mirror = use_mirror(g, n);
+    p.Rproc = mirror ? (g->rows + 1) / 2 : g->rows;
+    p.row_begin = row_begin;
+    p.row_end = row_end < 0 ? p.Rproc : row_end;
+    if (p.row_begin < 0 || p.row_end > p.Rproc || p.row_begin > p.row_end || p.row_begin % bp_tile_height(g->rows, g->cols))
+        return invalid("run_bp: bad row range (row_begin must be a multiple of the tile height)");
+    if (p.row_begin == p.row_end) return WT_OK;
+    if (mirror) {
+        if (n == 1) { if (!packed) launch_pack_sino<2, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
+        else { if (!packed) launch_pack_sino<4, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
         WT_CUDA(cudaGetLastError());
         return WT_OK;
     }
-    p.Rproc = g->rows;
     const Chunk c = chunk_of(n);
     switch (c.v) {
-    case 4: launch_pack_sino<4>(sino, sp, g, c.groups, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
-    case 2: launch_pack_sino<2>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
-    default: launch_pack_sino<1>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
+    case 4: if (!packed) launch_pack_sino<4>(sino, sp, g, c.groups, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
+    case 2: if (!packed) launch_pack_sino<2>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
+    default: if (!packed) launch_pack_sino<1>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
     }
     WT_CUDA(cudaGetLastError());
     return WT_OK;
@@ -501,6 +508,20 @@ int wt_mar_fp(const wt_geom *g, const float *vol, const float *b, const unsigned
 
 int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, float scale,
           void *ws, size_t ws_bytes, void *stream) {
+    return wt_bp_rows(g, sino, vol, nimages, angle_begin, angle_end, 0, -1, 0, scale, ws, ws_bytes, stream);
+}
+
+int wt_bp_row_info(const wt_geom *g, int nimages, int *rows_processed, int *row_align, int *mirrored) {
+    if (!g || nimages <= 0) return invalid("wt_bp_row_info: bad arguments");
+    const bool m = use_mirror(g, nimages);
+    if (rows_processed) *rows_processed = m ? (g->rows + 1) / 2 : g->rows;
+    if (row_align) *row_align = bp_tile_height(g->rows, g->cols);
+    if (mirrored) *mirrored = m ? 1 : 0;
+    return WT_OK;
+}
+
+int wt_bp_rows(const wt_geom *g, const float *sino, float *vol, int nimages, int angle_begin, int angle_end, int row_begin,
+               int row_end, int reuse_packed, float scale, void *ws, size_t ws_bytes, void *stream) {
     if (!g || !vol || !sino || !ws) return invalid("wt_bp: null pointer");
     if (nimages <= 0) return invalid("wt_bp: nimages must be positive");
     if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_bp: bad angle range");
@@ -512,7 +533,7 @@ int wt_bp(const wt_geom *g, const float *sino, float *vol, int nimages, int angl
     HBpStore epi;
     epi.vol = vol;
     epi.scale = scale;
-    return run_bp(g, sino, nimages, angle_begin, angle_end, sp, epi, (cudaStream_t)stream);
+    return run_bp(g, sino, nimages, angle_begin, angle_end, sp, epi, (cudaStream_t)stream, row_begin, row_end, reuse_packed != 0);
 }
 
 size_t wt_sirt_workspace_bytes(const wt_geom *g, int nimages) {

@@ -57,6 +57,7 @@ struct BpParams {
     int R, C, A;
     int nimg;         // images of this launch; the last group is padded with zero components up to V
     int Rproc;        // rows that get a thread: R, or ceil(R/2) under mirror pairing
+    int row_begin, row_end;   // of those, the rows this launch computes (row_begin is a multiple of the tile height)
     int padl, pitch;
     int a_begin, a_end;
 };
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     BpSmem<V, TH> &sm = *reinterpret_cast<BpSmem<V, TH> *>(smem_raw);
 
     const int g = blockIdx.z;
-    const int col0 = blockIdx.x * BP_TW, row0 = blockIdx.y * BP_TH;
-    const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.Rproc - row0);  // real pixels of this tile
+    const int col0 = blockIdx.x * BP_TW, row0 = p.row_begin + blockIdx.y * BP_TH;
+    const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.row_end - row0);  // real pixels of this tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nblk = (p.a_end - p.a_begin + BP_AB - 1) / BP_AB;
 
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int col = col0 + lane + 32 * c;
-            if (row < p.Rproc && col < p.C) {
+            if (row < p.row_end && col < p.C) {
                 if constexpr (MIRROR) {
                     constexpr int W = V / 2;
                     float direct[W], mirrored[W];
@@ -454,7 +455,7 @@ inline cudaError_t launch_bp_th(const BpParams &p, const Epi &epi, int groups, c
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.Rproc + TH - 1) / TH, groups);
+    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.row_end - p.row_begin + TH - 1) / TH, groups);
     bp_kernel<V, Epi, MIRROR, TH><<<grid, BP_BLOCK, smem, st>>>(p, epi);
     return cudaSuccess;
 }

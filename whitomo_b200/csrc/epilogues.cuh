@@ -323,8 +323,10 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
             v = v - prm.alpha * gt;
         }
         if (f.clip) {
-            v = fmaxf(v, 0.0f);
-            if (!f.lower_only) v = fminf(v, 1.0f);
+            // np.clip semantics: a NaN stays a NaN (fmaxf / fminf would turn it into the bound and hide the reference's
+            // own breakdown after a -1/0 barrier gradient, teeth_recon/experiments.py:737-749 at 1024^2)
+            v = v < 0.0f ? 0.0f : v;
+            if (!f.lower_only) v = v > 1.0f ? 1.0f : v;
         }
         xn[k] = v;
     }

@@ -33,15 +33,62 @@ def angle_ranges(n_angles, world, align=8):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
-class AngleSplit(object):
-    """W and W^T of one slice distributed over the ranks of `group` by angle range."""
+def angle_ranges_by_cost(tile_first, tile_count, n_angles, world, fp_share=0.55, tile_angles=8):
+    """Angle ranges per rank that balance the projector COST instead of the angle count.  The forward projector runs
+    one CTA column per angle tile whatever the tile holds (tiles around 45/135 degrees hold fewer than 8 angles: their
+    rays diverge faster than one staging window allows), the backprojector's cost is per angle.  With equal angle
+    counts the ranks around 45/135 degrees ran 8 % longer (profiles/r1_c5_anglesplit.json).  Cuts fall on tile
+    boundaries.  tile_first / tile_count: the plan of wt_geom_plan."""
+    cost = [fp_share * tile_angles + (1.0 - fp_share) * c for c in tile_count]
+    total = float(sum(cost))
+    cuts, acc, r = [0], 0.0, 1
+    for f, c, w in zip(tile_first, tile_count, cost):
+        # cut before this tile if that brings the running cost closer to the rank's share
+        while r < world and acc + 0.5 * w >= total * r / world:
+            cuts.append(f)
+            r += 1
+        acc += w
+    while len(cuts) < world:
+        cuts.append(n_angles)
+    cuts.append(n_angles)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
-    def __init__(self, proj, group=None):
+
+def plan_tiles(proj):
+    """(tile_first, tile_count) of the forward projector's angle tiles (host-only diagnostic wt_geom_plan)"""
+    import ctypes
+    from . import _capi
+    lib = _capi.load()
+    ang = proj.angles
+    mx = proj.nangles
+    first, count = (ctypes.c_int * mx)(), (ctypes.c_int * mx)()
+    nt = ctypes.c_int()
+    _capi.check(lib.wt_geom_plan(proj.rows, proj.cols, proj.ndet, proj.det_width,
+                                 ang.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), proj.nangles, mx,
+                                 first, count, None, None, ctypes.byref(nt), None, None))
+    return list(first[:nt.value]), list(count[:nt.value])
+
+
+class AngleSplit(object):
+    """W and W^T of one slice distributed over the ranks of `group` by angle range.
+
+    balance="cost" (default) cuts the angle list where the projector cost is equal (angle_ranges_by_cost),
+    "count" where the angle count is.  `bp` overlaps the sum of the partial backprojections with their computation:
+    the volume is backprojected in `bp_blocks` row blocks and every finished block goes into an asynchronous
+    all-reduce while the next block is computed; only the last block's reduction is exposed."""
+
+    def __init__(self, proj, group=None, balance="cost", bp_blocks=8):
         self.proj = proj
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.range = angle_ranges(proj.nangles, self.world)[self.rank]
+        self.bp_blocks = int(bp_blocks)
+        if balance == "cost" and self.world > 1 and hasattr(proj, "handle"):
+            first, count = plan_tiles(proj)
+            self.ranges = angle_ranges_by_cost(first, count, proj.nangles, self.world)
+        else:
+            self.ranges = angle_ranges(proj.nangles, self.world)
+        self.range = self.ranges[self.rank]
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -53,8 +100,26 @@ class AngleSplit(object):
         return self.proj.fp(x, angle_range=self.range)
 
     def bp(self, y, scale=1.0):
-        """W^T y: local partial backprojection of this rank's angles, then one all-reduce"""
-        return self._allreduce(self.proj.bp(y, angle_range=self.range, scale=scale))
+        """W^T y: local partial backprojection of this rank's angles, summed over the ranks.  Row block by row block
+        when the projector offers `bp_rows` (the all-reduce of a finished block runs while the next one is computed),
+        otherwise (the CPU stand-ins of the tests) one backprojection and one all-reduce."""
+        if self.world == 1 or self.bp_blocks <= 1 or not hasattr(self.proj, "bp_rows"):
+            return self._allreduce(self.proj.bp(y, angle_range=self.range, scale=scale))
+        import torch
+        lead = tuple(y.shape[:-2])
+        n = 1
+        for v in lead:
+            n *= v
+        out = torch.empty((n,) + tuple(self.proj.vol_shape), dtype=torch.float32, device=self.proj.device)
+        pending = []
+        for i, (b0, b1, written) in enumerate(self.proj.bp_row_blocks(n, self.bp_blocks)):
+            self.proj.bp_rows(y, out, b0, b1, angle_range=self.range, scale=scale, reuse_packed=i > 0)
+            for lo, hi in written:       # row ranges are contiguous only for one image: reduce image by image
+                for im in range(n):
+                    pending.append(dist.all_reduce(out[im, lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in pending:
+            w.wait()
+        return out.reshape(lead + tuple(self.proj.vol_shape))
 
     def white_func_grad(self, spectrum, conc, meas):
         """(loss, grad) of the white-beam data term with rays split by angle: loss and grad are all-reduced"""

@@ -166,6 +166,40 @@ class Projector(object):
                                    _stream()))
         return out.reshape(lead + self.vol_shape)
 
+    def bp_row_blocks(self, nimages, nblocks):
+        """Row blocks for `bp_rows`: list of (row_begin, row_end, [written row ranges]).  Blocks are aligned to the
+        backprojector's tile height; with mirror-paired single images (positions="exact") a block also writes its
+        point reflection, so it lists two row ranges."""
+        rp, al, mir = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _capi.check(self.lib.wt_bp_row_info(self.handle, int(nimages), ctypes.byref(rp), ctypes.byref(al), ctypes.byref(mir)))
+        rp, al, mir = rp.value, al.value, mir.value
+        per = -(-rp // max(1, nblocks))
+        per = -(-per // al) * al
+        out = []
+        for b0 in range(0, rp, per):
+            b1 = min(rp, b0 + per)
+            written = [(b0, b1)]
+            if mir:
+                lo, hi = self.rows - b1, self.rows - b0
+                lo = max(lo, b1) if lo < b1 else lo       # the middle row of an odd image is written once
+                if hi > lo:
+                    written.append((lo, hi))
+            out.append((b0, b1, written))
+        return out
+
+    @_on_own_device
+    def bp_rows(self, sino, out, row_begin, row_end, angle_range=None, scale=1.0, reuse_packed=False):
+        """rows [row_begin, row_end) of scale * W^T q written into `out` (n, rows, cols) (wt_bp_rows); the other rows
+        of `out` are left untouched.  Blocks come from `bp_row_blocks`."""
+        s, lead = self._as_images(sino, self.sino_shape)
+        n = s.shape[0]
+        a0, a1 = (0, self.nangles) if angle_range is None else angle_range
+        nbytes = self.lib.wt_workspace_bytes(self.handle, n)
+        ws = self._workspace(nbytes)
+        _capi.check(self.lib.wt_bp_rows(self.handle, _ptr(s), _ptr(out), n, int(a0), int(a1), int(row_begin), int(row_end),
+                                        int(bool(reuse_packed)), float(scale), _ptr(ws), nbytes, _stream()))
+        return out
+
     @_on_own_device
     def sirt(self, sino, n_iters=100):
         """ASTRA-style SIRT from x0 = 0; sino (..., nangles, ndet) -> (..., rows, cols)."""

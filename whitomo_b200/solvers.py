@@ -114,10 +114,11 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
 
 
 def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=1e-2, clip_concentrations=True,
-                    dissimilarity_constraint=True, triv_conc_constraint=True, alternate=True):
+                    dissimilarity_constraint=True, triv_conc_constraint=True, alternate=True, start_iter=0):
     """Plain gradient descent of src/white_rec.py:199-244,338-368 (flags as at :342-345, alpha/beta at :42-43):
     step = alpha*(grad + beta*(d|c0 c1| + c(c(4c-3)+1))); iteration i updates element 0 when i % 4 == 0 else
     element 1... (the reference zeroes step[1] when i % 4 == 0 and step[0] otherwise, :229-233); clip to [0, 1].
+    ``start_iter``: iteration number of the first step (a run continued from an earlier call keeps the alternation).
     Returns (c, losses) with losses[i] = ||q_i|| + ||beta c0 c1|| per slice (:236-237)."""
     K = spectrum.K
     c = _as_stack(c0, K)
@@ -125,7 +126,7 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
     meas = meas.reshape((S,) + proj.sino_shape).to(torch.float32).contiguous()
     losses = []
     mode = _capi.UPD_STEP_CLIP if clip_concentrations else _capi.UPD_STEP_ONLY
-    for it in range(n_iters):
+    for it in range(start_iter, start_iter + n_iters):
         _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
         g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
         reg_loss = 0.0
