@@ -77,7 +77,7 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
     p.R = g->rows; p.C = g->cols; p.D = g->ndet; p.A = g->nangles;
     p.a_begin = a_begin; p.a_end = a_end;
-    p.warp = g->d_warp; p.astra = g->positions == WT_POS_ASTRA;
+    p.warpf = g->d_warpf; p.astra = g->positions == WT_POS_ASTRA;
     p.Ex = -0.5f * (float)g->cols + 0.5f; p.Ey = 0.5f * (float)g->rows - 0.5f;
     p.order = g->d_order; p.nphase = g->nphase;
     static const bool tile_major = [] { const char *e = getenv("WT_FP_ORDER"); return e && !strcmp(e, "tile"); }();
@@ -127,7 +127,7 @@ template <class Epi>
 static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
                   cudaStream_t st, int row_begin = 0, int row_end = -1, bool packed = false) {
     BpParams p;
-    p.sp = sp; p.ang = g->d_bp; p.fang = g->d_fp; p.warp = g->d_warp;
+    p.sp = sp; p.bwarp = g->d_bwarp; p.bwarpd = g->d_bwarpd;
     p.R = g->rows; p.C = g->cols; p.A = g->nangles;
     p.padl = g->sino_padl; p.pitch = g->sino_pitch;
     p.a_begin = a_begin; p.a_end = a_end;
@@ -174,6 +174,9 @@ struct GeomPlan {
     std::vector<FpAngle> fp;
     std::vector<BpAngle> bp;
     std::vector<WarpAngle> warp;
+    std::vector<WarpAngleF> warpf;
+    std::vector<BpWarpF> bwarp;
+    std::vector<BpWarpD> bwarpd;
     std::vector<FpTile> tiles;
     std::vector<int> order;
     int phase_start[FP_MAX_PHASES + 1];
@@ -222,6 +225,9 @@ static int plan_geometry(int rows, int cols, int ndet, float det_width, const fl
     pl.fp.assign(nangles, FpAngle());
     pl.bp.assign(nangles, BpAngle());
     pl.warp.assign(nangles, WarpAngle());
+    pl.warpf.assign(nangles, WarpAngleF());
+    pl.bwarp.assign(nangles, BpWarpF());
+    pl.bwarpd.assign(nangles, BpWarpD());
     std::vector<FpAngle> &fp = pl.fp;
     std::vector<BpAngle> &bp = pl.bp;
     const double Ex = -0.5 * cols + 0.5, Ey = 0.5 * rows - 0.5;
@@ -265,6 +271,33 @@ static int plan_geometry(int rows, int cols, int ndet, float det_width, const fl
         b.b = (float)((double)f.len * fabs(f.c0_step));
         b.a1 = (float)((double)f.len - (double)f.len * fabs(f.c0_step));
         b.pad_ = 0.0f;
+        // float views of the warp for the kernels' searches
+        const WarpAngle &w = pl.warp[a];
+        WarpAngleF &wf = pl.warpf[a];
+        for (int i = 0; i < 16; ++i) { wf.gcum[i] = i < WT_NB ? (float)w.gcum[i] : 3.0e38f; wf.islope[i] = i < WT_NB ? (float)w.islope[i] : 1.0f; }
+        BpWarpF &bw = pl.bwarp[a];
+        const double s0 = w.gcum[5] / 64.0;
+        for (int m = 0; m < WT_NM; ++m) {
+            bw.cum[m] = m ? (float)w.gcum[m + 4] : 0.0f;
+            const double isl = m ? w.islope[m + 4] : 1.0 / s0, isl_prev = m > 1 ? w.islope[m + 3] : 1.0 / s0;
+            bw.bend[m] = m ? (float)fabs(isl - isl_prev) : 0.0f;
+        }
+        bw.a0 = b.a0;
+        bw.b = b.b;
+        for (int m = 0; m < WT_NM; ++m) {
+            bw.slope[m] = (float)(m ? w.slope[m + 4] : s0);
+            bw.isl[m] = (float)(m ? w.islope[m + 4] : 1.0 / s0);
+        }
+        bw.inv_step = (float)(1.0 / f.c0_step);
+        bw.delta = f.delta;
+        BpWarpD &bd = pl.bwarpd[a];
+        for (int m = 0; m < WT_NM; ++m) {
+            bd.cum[m] = m ? w.gcum[m + 4] : 0.0;
+            bd.slope[m] = m ? w.slope[m + 4] : s0;
+            bd.isl[m] = m ? w.islope[m + 4] : 1.0 / s0;
+        }
+        bd.c0_base = f.c0_base; bd.inv_step = 1.0 / f.c0_step; bd.delta = (double)f.delta;
+        bd.vertical = vertical; bd.pad_ = 0;
     }
     // angle tiles of the forward projector: consecutive angles of one orientation whose rays, over any
     // FP_DT-detector x FP_LB-line patch, stay within FP_WFIT positions of each other.  In exact arithmetic c_a - c_b is
@@ -384,7 +417,7 @@ int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
     g->sino_pitch = (padl + ndet + padl + BP_SEGW_MAX + 3) & ~3;
-    g->d_fp = nullptr; g->d_bp = nullptr; g->d_warp = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
+    g->d_fp = nullptr; g->d_bp = nullptr; g->d_warp = nullptr; g->d_warpf = nullptr; g->d_bwarp = nullptr; g->d_bwarpd = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
     g->nphase = nphase;
     for (int i = 0; i <= FP_MAX_PHASES; ++i) g->phase_start[i] = phase_start[i];
     g->ntiles = (int)tiles.size();
@@ -398,6 +431,12 @@ int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float
     if (e == cudaSuccess) e = cudaMemcpy(g->d_bp, bp.data(), sizeof(BpAngle) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_warp, sizeof(WarpAngle) * nangles);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_warp, pl.warp.data(), sizeof(WarpAngle) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_warpf, sizeof(WarpAngleF) * nangles);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_warpf, pl.warpf.data(), sizeof(WarpAngleF) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_bwarp, sizeof(BpWarpF) * nangles);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_bwarp, pl.bwarp.data(), sizeof(BpWarpF) * nangles, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_bwarpd, sizeof(BpWarpD) * nangles);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_bwarpd, pl.bwarpd.data(), sizeof(BpWarpD) * nangles, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_tiles, sizeof(FpTile) * tiles.size());
     if (e == cudaSuccess) e = cudaMemcpy(g->d_tiles, tiles.data(), sizeof(FpTile) * tiles.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_order, sizeof(int) * order.size());
@@ -415,6 +454,9 @@ void wt_geom_destroy(wt_geom *g) {
     if (g->d_fp) cudaFree(g->d_fp);
     if (g->d_bp) cudaFree(g->d_bp);
     if (g->d_warp) cudaFree(g->d_warp);
+    if (g->d_warpf) cudaFree(g->d_warpf);
+    if (g->d_bwarp) cudaFree(g->d_bwarp);
+    if (g->d_bwarpd) cudaFree(g->d_bwarpd);
     if (g->d_tiles) cudaFree(g->d_tiles);
     if (g->d_order) cudaFree(g->d_order);
     free(g->h_angles);

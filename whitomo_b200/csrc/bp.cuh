@@ -51,9 +51,8 @@ inline void launch_pack_sino(const float *sino, float *sp, const wt_geom *g, int
 
 struct BpParams {
     const float *sp;  // packed sinogram (G, A, pitch, V)
-    const BpAngle *ang;
-    const FpAngle *fang;     // the forward projector's constants of the same angles (c0_base, c0_step, delta)
-    const WarpAngle *warp;   // per angle: the reference's running sum as a position warp (identity under WT_POS_EXACT)
+    const BpWarpF *bwarp;    // per angle: K2's float view of the position warp + the tap-weight constants a0, b
+    const BpWarpD *bwarpd;   // per angle: the same in double + c0_base, 1/c0_step, delta (identity warp under WT_POS_EXACT)
     int R, C, A;
     int nimg;         // images of this launch; the last group is padded with zero components up to V
     int Rproc;        // rows that get a thread: R, or ceil(R/2) under mirror pairing
@@ -96,7 +95,8 @@ struct BpSmem {
     VecT seg[BP_STAGES][BP_AB][BpTile<TH>::SEGW];
     float4 cst[BP_STAGES][BP_AB];  // affine piece A of d*: dcol, drow, base - 1/2;  Ah = A0 - B/2
     float4 cst2[BP_STAGES][BP_AB]; // affine piece B of d*: dcol, drow, base - 1/2;  Ah of piece B
-    float4 cst3[BP_STAGES][BP_AB]; // B of piece A, B of piece B, flags (BP_F_*), unused
+    float2 cst3[BP_STAGES][BP_AB]; // B of piece A, flags (BP_F_*)
+    float cst4[BP_STAGES][BP_AB];  // B of piece B
     uint64_t full[BP_STAGES];   // TMA bytes of a stage have landed
     uint64_t empty[BP_STAGES];  // all consumer warps are done reading a stage
 };
@@ -135,115 +135,131 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     }
     __syncthreads();
 
-    // producer warp: stage angle block `blk`
-    auto produce = [&](int blk) {
-        const int s = blk % BP_STAGES;
+    // Producer warp: lane = one angle of the block.  plan() computes the angle's constants for this tile into registers
+    // -- BEFORE the producer waits for the stage to be released, so the arithmetic is off the refill path -- and
+    // issue() publishes them and starts the TMA copy of the angle's sinogram segment.
+    //
+    // Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
+    //     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
+    // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two; over
+    // positions [0, 64) G is replaced by its secant, common.cuh: BpWarpF), so z = G(k) - l * delta is affine over the
+    // tile.  Ginv is piecewise affine in z with kinks where a ray STARTED on a binade boundary; the tile's z-range
+    // (< 97 wide) usually holds none that matters (2-7 % of the tile x angle pairs at 8192^2 do): d* is then the max (or
+    // min) of two affine pieces.  The stripe searches run in float on a 96-byte table per angle; only the pieces that
+    // were picked are evaluated in double.
+    struct Plan { float4 c4, c5; float2 c6; float bB; const VecT *src; };
+    auto plan = [&](int blk) {
+        Plan pl;
+        pl.src = nullptr;
         const int a = p.a_begin + blk * BP_AB + lane;
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
-        const VecT *src = nullptr;
         if (lane < nvalid) {
-            // Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
-            //     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
-            // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two;
-            // over positions [0, 64) G is replaced by its secant, see below), so
-            // z = G(k) - l * delta is affine over the tile.  Ginv is piecewise affine in z with kinks where a ray
-            // STARTED on a binade boundary; the tile's z-range (< 97 wide) usually holds none that matters (2-7 % of
-            // the tile x angle pairs at 8192^2 do): d* is then the max (or min) of two affine pieces.
-            const BpAngle an = p.ang[a];
-            const FpAngle fa = p.fang[a];
-            const WarpAngle *w = p.warp + a;
-            // K2's view of the warp: the stripes below 64 merged into one with the secant slope G(64) / 64 (used for G
-            // and Ginv alike, so the two stay inverse to each other): merged stripe 0 = [0, 64), m >= 1 = stripe m + 4
-            constexpr int NM = WT_NB - 4;
-            const double s0 = __ldg(&w->gcum[5]) * (1.0 / 64.0);
-            auto m_pos = [&](int m) { return m ? stripe_pos(m + 4) : 0.0; };
-            auto m_cum = [&](int m) { return m ? __ldg(&w->gcum[m + 4]) : 0.0; };
-            auto m_slope = [&](int m) { return m ? __ldg(&w->slope[m + 4]) : s0; };
-            auto m_isl = [&](int m) { return m ? __ldg(&w->islope[m + 4]) : 1.0 / s0; };
-            const bool vert = fa.vertical != 0;
+            const BpWarpF *wf = p.bwarp + a;
+            const BpWarpD *w = p.bwarpd + a;
+            const bool vert = __ldg(&w->vertical) != 0;
             const int k0 = vert ? col0 : row0, l0 = vert ? row0 : col0;
             const int nk = vert ? tw : th, nl = vert ? th : tw;
-            int ik = 0;
-            for (int m = 1; m < NM; ++m)
-                if ((double)k0 >= m_pos(m)) ik = m;
-            const double sk = m_slope(ik);
-            const double gk0 = m_cum(ik) + ((double)k0 - m_pos(ik)) * sk;
-            const double dl = (double)fa.delta;
-            const double za = gk0 - (double)l0 * dl, zk = sk * (double)(nk - 1), zl = -dl * (double)(nl - 1);
-            const double zlo = za + fmin(0.0, zk) + fmin(0.0, zl), zhi = za + fmax(0.0, zk) + fmax(0.0, zl);
-            const double zc = 0.5 * (zlo + zhi);
-            // piece A: the stripe of the tile centre; piece B: across the kink inside (zlo, zhi) that bends d* most
-            int ia = 0;
-            for (int m = 1; m < NM; ++m)
-                if (fabs(zc) >= m_cum(m)) ia = m;
-            const double sgn_a = zc < 0.0 ? -1.0 : 1.0;
+            const int ik = k0 < 64 ? 0 : min(WT_NM - 1, 26 - __clz(k0));      // floor(log2 k0) - 5
+            const float skf = __ldg(&wf->slope[ik]), iskf = __ldg(&wf->isl[ik]), dlf = __ldg(&wf->delta);
+            const float istep = __ldg(&wf->inv_step);
+            // z of the tile origin in double (the one quantity that needs it: d* to 1e-5 at |z| ~ 1e4) ...
+            const double za = __ldg(&w->cum[ik]) + (double)(k0 - (ik ? (32 << ik) : 0)) * __ldg(&w->slope[ik]) - (double)l0 * __ldg(&w->delta);
+            // ... the tile's extent and the stripe searches in float
+            const float zaf = (float)za, zk = skf * (float)(nk - 1), zl = -dlf * (float)(nl - 1);
+            const float zlo = zaf + fminf(0.0f, zk) + fminf(0.0f, zl), zhi = zaf + fmaxf(0.0f, zk) + fmaxf(0.0f, zl);
+            const float zc = 0.5f * (zlo + zhi), azc = fabsf(zc);
+            // piece A: the stripe of the tile centre (G's edges lie within 0.1 % of the powers of two, except beyond a
+            // stripe where the reference's rays stand still: walk from the power-of-two guess)
+            int ia = azc < 64.0f ? 0 : min(WT_NM - 1, (int)((__float_as_uint(azc) >> 23) & 0xffu) - 127 - 5);
+            while (ia > 0 && azc < __ldg(&wf->cum[ia])) --ia;
+            while (ia + 1 < WT_NM && azc >= __ldg(&wf->cum[ia + 1])) ++ia;
+            const bool negc = zc < 0.0f;
+            // piece B: across the kink inside (zlo, zhi) that bends d* most -- the edges of A's stripe on the centre's
+            // side of zero, and the first edge on the other side if the range straddles zero (a range is < 97 wide)
             int ib = ia;
-            double sgn_b = sgn_a, worst = 5.0e-5;                              // kinks that bend d* by less are ignored
-            bool b_high = false;                                               // piece B lies at larger z than the centre
-            for (int m = 1; m < NM; ++m) {
-                const double gb = m_cum(m);
-                const double bend = fabs(m_isl(m) - m_isl(m - 1));
-                for (int sg = 0; sg < 2; ++sg) {
-                    const double zb = sg ? -gb : gb;
-                    if (zb <= zlo || zb >= zhi) continue;
-                    const double far_side = zb > zc ? zhi - zb : zb - zlo;     // extent on the side away from the centre
-                    if (bend * far_side > worst) {
-                        worst = bend * far_side;
-                        // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
-                        const bool outward = sg ? (zb < zc) : (zb > zc);
-                        ib = outward ? m : m - 1;
-                        sgn_b = sg ? -1.0 : 1.0;
-                        b_high = zb > zc;
-                    }
+            bool negb = negc, b_high = false;                                  // b_high: B lies at larger z than the centre
+            float worst = 5.0e-5f;                                             // kinks that bend d* by less are ignored
+            auto consider = [&](int m, bool neg) {
+                if (m < 1 || m >= WT_NM) return;
+                const float edge = __ldg(&wf->cum[m]), zb = neg ? -edge : edge;
+                const float far_side = zb > zc ? zhi - zb : zb - zlo;          // extent on the side away from the centre
+                const float w_ = __ldg(&wf->bend[m]) * far_side;
+                if (zb > zlo && zb < zhi && w_ > worst) {
+                    worst = w_;
+                    // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
+                    const bool outward = neg ? (zb < zc) : (zb > zc);
+                    ib = outward ? m : m - 1;
+                    negb = neg;
+                    b_high = zb > zc;
                 }
-            }
-            // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i
-            const double inv_step = 1.0 / fa.c0_step;
-            auto piece = [&](double sgn, int i, double &d_t00, double &dk, double &dll) {
-                const double isl = m_isl(i);
-                d_t00 = (sgn * m_pos(i) + (za - sgn * m_cum(i)) * isl - fa.c0_base) * inv_step - 0.5;
-                dk = sk * isl * inv_step;
-                dll = -dl * isl * inv_step;
             };
-            double tA, kA, lA, tB, kB, lB;
-            piece(sgn_a, ia, tA, kA, lA);
-            piece(sgn_b, ib, tB, kB, lB);
-            // beyond the kink piece B is the right one: d* = max(A, B) if B lies above A there, else min(A, B)
-            const double kf = (double)(nk - 1), lf = (double)(nl - 1);
-            double dmin = 1e300;
-            bool use_max = true;
-            {
-                // corner of the tile furthest into B's side in z
-                const double ck = (zk > 0.0) == b_high ? kf : 0.0, cl = (zl > 0.0) == b_high ? lf : 0.0;
-                use_max = (tB + ck * kB + cl * lB) >= (tA + ck * kA + cl * lA);
+            consider(ia, negc);
+            consider(ia + 1, negc);
+            if (ia == 0) consider(1, !negc);
+            const bool kink = !(ib == ia && negb == negc);
+            // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i;  d* at the tile origin in
+            // double, then relative to an integer near it in float; the slopes of d* in float
+            const double c0_base = __ldg(&w->c0_base), inv_step = __ldg(&w->inv_step);
+            auto origin = [&](bool neg, int i) {
+                const double pos = i ? (double)(32 << i) : 0.0, cum = __ldg(&w->cum[i]);
+                return ((neg ? -pos : pos) + (za - (neg ? -cum : cum)) * __ldg(&w->isl[i]) - c0_base) * inv_step - 0.5;
+            };
+            const double tA = origin(negc, ia);
+            const int ibase = __double2int_rd(tA);
+            const float islA = __ldg(&wf->isl[ia]), islB = __ldg(&wf->isl[ib]);
+            const float tAf = (float)(tA - (double)ibase), kA = skf * islA * istep, lA = -dlf * islA * istep;
+            float tBf = tAf, kB = kA, lB = lA;
+            if (kink) {
+                tBf = (float)(origin(negb, ib) - (double)ibase);
+                kB = skf * islB * istep;
+                lB = -dlf * islB * istep;
             }
+            // beyond the kink piece B is the right one: d* = max(A, B) if B lies above A there, else min(A, B)
+            const float kf = (float)(nk - 1), lf = (float)(nl - 1);
+            bool use_max = true;
+            if (kink) {      // corner of the tile furthest into B's side in z
+                const float ck = (zk > 0.0f) == b_high ? kf : 0.0f, cl = (zl > 0.0f) == b_high ? lf : 0.0f;
+                use_max = (tBf + ck * kB + cl * lB) >= (tAf + ck * kA + cl * lA);
+            }
+            float dmin = 3.0e38f;
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const double ck = (c & 1) ? kf : 0.0, cl = (c & 2) ? lf : 0.0;
-                const double va = tA + ck * kA + cl * lA, vb = tB + ck * kB + cl * lB;
-                dmin = fmin(dmin, use_max ? fmax(va, vb) : fmin(va, vb));
+                const float ck = (c & 1) ? kf : 0.0f, cl = (c & 2) ? lf : 0.0f;
+                const float va = tAf + ck * kA + cl * lA, vb = tBf + ck * kB + cl * lB;
+                dmin = fminf(dmin, use_max ? fmaxf(va, vb) : fminf(va, vb));
             }
             // B = len * |dc/dd| at fixed line: the rays' spacing on the pixel line, i.e. their spacing at the start
             // stretched by the warp between the start stripe and the tile's stripe
-            const double bA = (double)an.b * (m_slope(ia) / sk), bB = (double)an.b * (m_slope(ib) / sk);
-            const bool kink = !(ib == ia && sgn_b == sgn_a);
+            const float a0 = __ldg(&wf->a0), bnom = __ldg(&wf->b);
+            const float bA = bnom * (__ldg(&wf->slope[ia]) * iskf), bB = kink ? bnom * (__ldg(&wf->slope[ib]) * iskf) : bA;
             // rays closer than a position: a third ray can reach a pixel (weight up to len - B)
-            const bool four = fmin(bA, bB) < 0.9985 * (double)an.a0;
-            const bool mild = fabs(m_isl(ia) - m_isl(ib)) < 3.0e-4 * m_isl(ia);
+            const bool four = fminf(bA, bB) < 0.9985f * a0;
+            const bool mild = !kink || fabsf(islA - islB) < 3.0e-4f * islA;
             const bool generic = four || (kink && !mild);
             const int flags = (generic ? BP_F_GENERIC : 0) | (kink && !generic ? BP_F_KINK : 0) | (kink && !use_max ? BP_F_MIN : 0) |
                               (four ? BP_F_FOUR : 0);
-            const int lo = (int)floor(dmin) - (four ? 2 : 1) + p.padl;  // >= 0 by construction of padl
+            // segment start (one slot of slack below the smallest d*: the shared pairs look one tap down)
+            const int lo = ibase + (int)floorf(dmin - 1.0e-3f) - (four ? 2 : 1) + p.padl;  // >= 0 by construction of padl
             const int aligned = lo & ~3;
             // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
             // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
-            const double off = (double)(p.padl - aligned) - 0.5;
-            sm.cst[s][lane] = make_float4((float)(vert ? kA : lA), (float)(vert ? lA : kA), (float)(tA + off), (float)((double)an.a0 - 0.5 * bA));
-            if (!kink)                           // piece B = piece A
-                sm.cst2[s][lane] = sm.cst[s][lane];
-            else
-                sm.cst2[s][lane] = make_float4((float)(vert ? kB : lB), (float)(vert ? lB : kB), (float)(tB + off), (float)((double)an.a0 - 0.5 * bB));
-            sm.cst3[s][lane] = make_float4((float)bA, (float)bB, __int_as_float(flags), 0.0f);
-            src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
+            const float off = (float)(ibase + p.padl - aligned) - 0.5f;
+            pl.c4 = make_float4(vert ? kA : lA, vert ? lA : kA, tAf + off, a0 - 0.5f * bA);
+            pl.c5 = make_float4(vert ? kB : lB, vert ? lB : kB, tBf + off, a0 - 0.5f * bB);
+            pl.c6 = make_float2(bA, __int_as_float(flags));
+            pl.bB = bB;
+            pl.src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
+        }
+        return pl;
+    };
+    auto issue = [&](int blk, const Plan &pl) {
+        const int s = blk % BP_STAGES;
+        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        if (lane < nvalid) {
+            sm.cst[s][lane] = pl.c4;
+            sm.cst2[s][lane] = pl.c5;
+            sm.cst3[s][lane] = pl.c6;
+            sm.cst4[s][lane] = pl.bB;
         }
         __syncwarp();
         if (lane == 0) {
@@ -251,14 +267,15 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
         }
         __syncwarp();
-        if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
+        if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], pl.src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
     };
 
     if (warp == BP_THREADS / 32) {
         // runs ahead of the consumers by up to BP_STAGES angle blocks; consumer warps never wait for each other
         for (int blk = 0; blk < nblk; ++blk) {
+            const Plan pl = plan(blk);
             if (blk >= BP_STAGES) mbar_wait(&sm.empty[blk % BP_STAGES], (uint32_t)(((blk / BP_STAGES) - 1) & 1));
-            produce(blk);
+            issue(blk, pl);
         }
         return;
     }
@@ -287,15 +304,16 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         f = ds - (t - MAGIC);                  // frac(d*) - 1/2
         idx = __float_as_int(t) - MAGIC_BITS;
     };
+    // (`seg` minus MAGIC_BITS elements, indexed with the raw bits of the rounded sum: one LEA per tap address)
     auto single = [&](float ds, const float4 &c4, float bw, const VecT *seg, float (&a)[V]) {
-        int idx;
-        float f;
-        locate(ds, idx, f);
-        check_index(idx, idx + 1, BP_SEGW);
+        const float t = ds + MAGIC;            // round(d* - 1/2) = floor(d*) (ties: the extra tap has weight 0)
+        const float f = ds - (t - MAGIC);      // frac(d*) - 1/2
+        check_index(__float_as_int(t) - MAGIC_BITS, __float_as_int(t) - MAGIC_BITS + 1, BP_SEGW);
+        const VecT *tap = (seg - MAGIC_BITS) + __float_as_int(t);
         const float w0 = fmaxf(0.0f, fmaf(-bw, f, c4.w)), w1 = fmaxf(0.0f, fmaf(bw, f, c4.w));
         float v0[V], v1[V];
-        unpack<V>(seg[idx], v0);
-        unpack<V>(seg[idx + 1], v1);
+        unpack<V>(tap[0], v0);
+        unpack<V>(tap[1], v1);
         tap_pair_fma<V>(w0, v0, w1, v1, a);
     };
     // A vertically adjacent pixel pair with shared taps (float4 kernels).  The upper pixel is located as `single`
@@ -359,8 +377,7 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     // Generic path (BP_F_GENERIC): d* = max or min of the two affine pieces, each pixel located on its own with the tap
     // spacing of the piece it falls on; with BP_F_FOUR the two outer candidates idx - 1 and idx + 2 get their weights
     // max(0, len - B * distance) too (they vanish unless the rays are closer than a position).
-    auto one_angle_generic = [&](const float4 &c4, const float4 &c5, const float4 &c6, const VecT *seg) {
-        const int flags = __float_as_int(c6.z);
+    auto one_angle_generic = [&](const float4 &c4, const float4 &c5, float bwa, float bwb, int flags, const VecT *seg) {
         const bool use_min = (flags & BP_F_MIN) != 0, four = (flags & BP_F_FOUR) != 0;
 #pragma unroll
         for (int r = 0; r < BP_RPT; ++r) {
@@ -369,7 +386,7 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             for (int c = 0; c < 2; ++c) {
                 const float da = fmaf(jc[c], c4.x, dra), db = fmaf(jc[c], c5.x, drb);
                 const bool on_b = use_min ? (db < da) : (db > da);
-                const float ds = on_b ? db : da, bw = on_b ? c6.y : c6.x, ah = on_b ? c5.w : c4.w;
+                const float ds = on_b ? db : da, bw = on_b ? bwb : bwa, ah = on_b ? c5.w : c4.w;
                 int idx;
                 float f;
                 locate(ds, idx, f);
@@ -394,18 +411,19 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
         const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
-            const float4 c4 = sm.cst[s][k], c6 = sm.cst3[s][k];
+            const float4 c4 = sm.cst[s][k];
+            const float2 c6 = sm.cst3[s][k];
             const VecT *seg = &sm.seg[s][k][0];
-            const int flags = __float_as_int(c6.z);
-            if (flags & BP_F_GENERIC) one_angle_generic(c4, sm.cst2[s][k], c6, seg);
+            const int flags = __float_as_int(c6.y);
+            if (flags == 0) {       // the common case first
+                if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), std::false_type(), c4, c4, false, c6.x, seg);
+                else one_angle(std::false_type(), std::false_type(), c4, c4, false, c6.x, seg);
+            } else if (flags & BP_F_GENERIC) one_angle_generic(c4, sm.cst2[s][k], c6.x, sm.cst4[s][k], flags, seg);
             else if (flags & BP_F_KINK) {
                 const float4 c5 = sm.cst2[s][k];
                 const bool use_min = (flags & BP_F_MIN) != 0;
                 if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), std::true_type(), c4, c5, use_min, c6.x, seg);
                 else one_angle(std::false_type(), std::true_type(), c4, c5, use_min, c6.x, seg);
-            } else {
-                if (BpShare<V>::value == 0 || c4.y >= 0.0f) one_angle(std::true_type(), std::false_type(), c4, c4, false, c6.x, seg);
-                else one_angle(std::false_type(), std::false_type(), c4, c4, false, c6.x, seg);
             }
         }
         __syncwarp();

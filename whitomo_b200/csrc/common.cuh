@@ -85,6 +85,33 @@ struct WarpAngle {
     double slope[WT_NB];    // dG/dc inside stripe i = delta / step_i
     double islope[WT_NB];   // 1 / slope
 };
+// float copies for the kernels' searches: the fine table (K1's staging windows and line ranges) ...
+struct WarpAngleF {
+    float gcum[16];
+    float islope[16];     // entries [WT_NB, 16) are padding
+};
+// ... and K2's view: the stripes below 64 merged into one with the secant slope G(64) / 64 (used for G and Ginv alike, so
+// the two stay inverse to each other): merged stripe 0 = [0, 64), m >= 1 = stripe m + 4.  cum[m] = G at the lower edge,
+// bend[m] = |1/slope_m - 1/slope_(m-1)| (how much d* bends at that edge); a0, b: the tap-weight constants of the angle.
+constexpr int WT_NM = WT_NB - 4;
+struct BpWarpF {
+    float cum[WT_NM];
+    float a0;
+    float bend[WT_NM];
+    float b;
+    float slope[WT_NM];
+    float inv_step;         // 1 / c0_step
+    float isl[WT_NM];       // 1 / slope
+    float delta;
+};
+// the same merged view in double, with everything else K2's producer needs of an angle (no division on the device)
+struct BpWarpD {
+    double cum[WT_NM];
+    double slope[WT_NM];
+    double isl[WT_NM];      // 1 / slope
+    double c0_base, inv_step, delta;
+    int vertical, pad_;
+};
 __host__ __device__ inline double stripe_pos(int i) { return i == 0 ? 0.0 : (double)(2 << i); }
 __host__ __device__ inline int stripe_of(double a) {   // a >= 0
     int i = 0;
@@ -117,6 +144,9 @@ struct wt_geom {
     wt::FpAngle *d_fp;
     wt::BpAngle *d_bp;
     wt::WarpAngle *d_warp;   // per angle: the reference's float32 running sum as a position warp (identity under WT_POS_EXACT)
+    wt::WarpAngleF *d_warpf; // float copy for K1
+    wt::BpWarpF *d_bwarp;    // merged float view for K2
+    wt::BpWarpD *d_bwarpd;   // ... and its double version
     int positions;           // WT_POS_ASTRA | WT_POS_EXACT
     void *d_tiles;   // wt::FpTile[ntiles]: angle tiles of the forward projector
     int ntiles;

@@ -127,7 +127,7 @@ struct FpParams {
     int nimg;          // images of this launch; the last group is padded with zero components up to V
     int Dproc;         // detectors that get a thread: D, or ceil(D/2) under mirror pairing
     int a_begin, a_end;
-    const WarpAngle *warp;   // per angle (identity under WT_POS_EXACT)
+    const WarpAngleF *warpf; // per angle: float copy of the position warp (identity under WT_POS_EXACT)
     int astra;               // 1: positions are the reference's float32 running sums (WT_POS_ASTRA)
     float Ex, Ey;            // -C/2 + 1/2, R/2 - 1/2 as float32 (ASTRA's volume corner)
     // CTA launch order (see fp_block): tiles grouped into phases (one per orientation)
@@ -193,7 +193,7 @@ struct FpSmem {
     uint64_t empty[FP_STAGES];  // all consumer warps are done reading a stage
     float wstart[FP_STAGES];
     float zmin[FP_AT], delta[FP_AT];   // per angle of the tile: left-most ray at line 0 in unwarped coordinates, slope
-    float gcum[FP_AT][WT_NB], islope[FP_AT][WT_NB];   // the angles' position warps (float copies)
+    alignas(16) WarpAngleF wtab[FP_AT];   // the angles' position warps (stored as float4)
     int lo, hi;                                    // line range any ray of the CTA needs
 };
 
@@ -257,25 +257,25 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         sm.lo = nlines;
         sm.hi = 0;
     }
+    if (tid < FP_AT * 8 && (tid >> 3) < tile.count)      // the angles' position warps: 8 x 16 bytes per angle
+        reinterpret_cast<float4 *>(&sm.wtab[tid >> 3])[tid & 7] = __ldg(reinterpret_cast<const float4 *>(p.warpf + tile.first + (tid >> 3)) + (tid & 7));
+    __syncthreads();
     if (tid < FP_AT) {
-        // this angle's position warp, and the left-most of the tile's rays of this angle at line 0 (detectors
-        // d0 .. min(d0+DT, D)-1) in unwarped coordinates (G is increasing: the left-most ray stays the left-most)
+        // the left-most of the tile's rays of this angle at line 0 (detectors d0 .. min(d0+DT, D)-1) in unwarped
+        // coordinates (G is increasing: the left-most ray stays the left-most)
         float lo_z = 3.0e38f, dl = 0.0f;
         const int aa = tile.first + tid;
         if (tid < tile.count) {
             const FpAngle an = p.ang[aa];
-            const WarpAngle *w = p.warp + aa;
-            for (int i = 0; i < WT_NB; ++i) { sm.gcum[tid][i] = (float)__ldg(&w->gcum[i]); sm.islope[tid][i] = (float)__ldg(&w->islope[i]); }
             const int dl_ = min(d0 + FP_DT, p.Dproc) - 1;
             const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
             const double cb = an.c0_base + ((double)dl_ + 0.5) * an.c0_step;
-            lo_z = warp_g_f(sm.gcum[tid], sm.islope[tid], (float)fmin(ca, cb));
+            lo_z = warp_g_f(sm.wtab[tid].gcum, sm.wtab[tid].islope, (float)fmin(ca, cb));
             dl = an.delta;
         }
         sm.zmin[tid] = lo_z;
         sm.delta[tid] = dl;
     }
-    __syncthreads();
 
     float c0h = 0.0f, delta = 0.0f, len = 0.0f, c_run = 0.0f;
     int l_lo = 0, l_hi = 0;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         // lines on which floor(c) can be inside [-1, npos-1], from the warped closed form G(c_l) = G(c_0) + l delta;
         // the estimate may be off by a line on each side (and by the 5e-3 pixel residual of the warp), which the
         // zero padding absorbs (|delta| <= 1, VPAD = 4)
-        const float *gc = sm.gcum[slot], *is = sm.islope[slot];
+        const float *gc = sm.wtab[slot].gcum, *is = sm.wtab[slot].islope;
         const float z0 = warp_g_f(gc, is, c0), zn = warp_g_f(gc, is, (float)npos);
         if (fabsf(delta) * (float)nlines < 0.5f) {
             const bool hit = (c0 > -2.0f) && (c0 < (float)npos + 1.0f);
@@ -322,18 +322,20 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     const bool tile_in_range = tile.first < p.a_end && tile.first + tile.count > p.a_begin;   // CTA-uniform
     const int nchunk = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
 
-    // producer warp: stage chunk `ch` = the ch-th chunk of FP_LB lines (ascending, the reference's summation order)
-    auto produce = [&](int ch) {
-        const int s = ch % FP_STAGES;
+    // producer warp: where the window of chunk `ch` (the ch-th chunk of FP_LB lines, ascending: the reference's
+    // summation order) starts -- computed BEFORE the producer waits for the stage to be released
+    auto plan = [&](int ch) {
         const int l0 = Lb + ch * FP_LB;
         const int l1 = min(l0 + FP_LB, nlines) - 1;
-        // left-most position any ray of the tile takes on these lines (linear in l: attained at an end)
+        // left-most position any ray of the tile takes on these lines (monotone in l: attained at an end)
         float m = 3.0e38f;
         if (lane < FP_AT) {
             const float zm = sm.zmin[lane], dl = sm.delta[lane];
-            if (zm < 1.0e38f)
-                m = fminf(warp_ginv_f(sm.gcum[lane], sm.islope[lane], fmaf((float)l0, dl, zm)),
-                          warp_ginv_f(sm.gcum[lane], sm.islope[lane], fmaf((float)l1, dl, zm)));
+            if (zm < 1.0e38f) {
+                const float za = fmaf((float)l0, dl, zm), zb = fmaf((float)l1, dl, zm);
+                if (p.astra) m = fminf(warp_ginv_f(sm.wtab[lane].gcum, sm.wtab[lane].islope, za), warp_ginv_f(sm.wtab[lane].gcum, sm.wtab[lane].islope, zb));
+                else m = fminf(za, zb);          // the warp is the identity
+            }
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -341,8 +343,12 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         int ws = (int)floorf(m) - 2;
         ws = max(ws, -VPAD);
         ws = min(ws, pitch - VPAD - FP_W);
-        ws = (ws + VPAD) & ~(4 / V - 1);            // slot index (>= 0), 16-byte aligned
-        const int nl = l1 - l0 + 1;
+        return (ws + VPAD) & ~(4 / V - 1);          // slot index (>= 0), 16-byte aligned
+    };
+    auto issue = [&](int ch, int ws) {
+        const int s = ch % FP_STAGES;
+        const int l0 = Lb + ch * FP_LB;
+        const int nl = min(l0 + FP_LB, nlines) - l0;
         if (lane == 0) {
             fence_proxy_async();                     // consumers' generic-proxy reads of this stage precede the refill
             sm.wstart[s] = (float)(ws - VPAD);       // position of window slot 0
@@ -364,8 +370,9 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         // runs ahead of the consumers by up to FP_STAGES chunks; a stage is refilled as soon as all 8 consumer
         // warps have released it -- consumer warps never wait for each other, only for data
         for (int ch = 0; ch < nchunk; ++ch) {
+            const int ws = plan(ch);
             if (ch >= FP_STAGES) mbar_wait(&sm.empty[ch % FP_STAGES], (uint32_t)(((ch / FP_STAGES) - 1) & 1));
-            produce(ch);
+            issue(ch, ws);
         }
     } else if (!MIRROR && p.astra) {
         // the reference's running sum: c at line l is c_0 after l float32 additions of delta.  Lines before the ray
