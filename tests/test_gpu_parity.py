@@ -184,9 +184,10 @@ def test_white_fp_vs_reference_module_golden(eng, golden, tag):
     assert rel_l2(inten.cpu().numpy().ravel(), z[tag + "_I"]) < TOL_OP
     assert abs(loss.item() - float(z[tag + "_func"])) < 1e-4 * float(z[tag + "_func"])
     q = z[tag + "_sinogram"] - z[tag + "_I"]
-    assert rel_l2(qmu[0].cpu().numpy().reshape(2, -1), q * z[tag + "_mu"]) < 5e-4
+    # measured 5e-7 (q mu) and 2e-6 (gradient): profiles/r2_test_margins.json
+    assert rel_l2(qmu[0].cpu().numpy().reshape(2, -1), q * z[tag + "_mu"]) < TOL_OP
     grad = -P.bp(qmu[0]).cpu().numpy()
-    assert rel_l2(grad, z[tag + "_grad"]) < 5e-4
+    assert rel_l2(grad, z[tag + "_grad"]) < TOL_OP
 
 
 def test_white_fp_stack_and_odd_k(eng, golden):

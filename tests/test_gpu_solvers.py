@@ -70,12 +70,12 @@ def test_white_projection_class_vs_reference_module(golden, tag):
     f = wp.func(c)
     assert abs(f - float(z[tag + "_func"])) < 1e-4 * float(z[tag + "_func"])
     g = wp.grad(c)
-    assert g.dtype == np.float64 and g.shape == c.shape and rel_l2(g, z[tag + "_grad"]) < 5e-4
+    assert g.dtype == np.float64 and g.shape == c.shape and rel_l2(g, z[tag + "_grad"]) < TOL_OP
     I, exp_arg, exp, flat_fp = wp.FP_white(c)
     assert I.shape == (wp.proj_shape[0] * wp.proj_shape[1],) and flat_fp.shape == (2, I.shape[0], 1)
     assert rel_l2(I, z[tag + "_I"]) < TOL_OP and rel_l2(wp.calc_mu(exp), z[tag + "_mu"]) < TOL_OP
     conc, mu = wp.BP_white(wp.sinogram - I, exp)
-    assert rel_l2(conc, z[tag + "_grad"]) < 5e-4
+    assert rel_l2(conc, z[tag + "_grad"]) < TOL_OP
     assert rel_l2(wp.FP(c[0]), oracle.fp(oracle.Geometry.standard(n, na), c[0])) < TOL_OP
 
 
@@ -119,6 +119,46 @@ def test_white_barrier_stack_vs_reference_golden(golden):
     assert info["iters"] > 0 and torch.isfinite(info["loss"]).all()
 
 
+def test_fused_loop_statistics_callback_has_the_reference_format(golden):
+    """add_stat_cb of the fused loop receives (goal_stat, reg_stats, bf_stats) of StepStat(x, func, grad) like the
+    reference's (src/barrier_method.py:182-199): goal func = f(x), goal grad = the TOTAL gradient (B5), the named
+    regulariser and barrier entries of src/barrier_method_gogo.py:79-94 -- checked against the oracle's driver"""
+    from whitomo_b200.projector import Projector, Spectrum
+    from whitomo_b200 import solvers
+    from whitomo_b200.barrier_method import StepStat
+    z = golden("barrier_white")
+    n, na = int(z["n"]), int(z["n_angles"])
+    grid = z["grid"]
+    wo = ow.WhiteOracle(z["source"], float(z["pixel_size"]), z["ea"], grid, (n, n), n_angles=na)
+    wo.calc_sinogram_with_gt(z["gt"])
+    ir_beta = float(z["ir_beta"])
+    p = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+    ref = []
+    ineq_reg = (lambda x: ir_beta * np.abs(x[0] * x[1]), lambda x: ir_beta * ow.calc_uneq_reg_grad(x))
+    nonneg = (lambda x: -x, lambda x: -np.ones_like(x), lambda x: np.clip(x, 0, x.max()))
+    le_one = (lambda x: x - 1, lambda x: np.ones_like(x), lambda x: np.clip(x, x.min(), 1))
+    ob.barrier_method(z["x0"].copy(), (wo.func, wo.grad), reg_dict={"ineq_reg": ineq_reg},
+                      ineq_dict={"conc_non_negative": nonneg, "conc_less_than_one": le_one}, add_stat_cb=ref.append, **p)
+    P = Projector(n, n, wo.geom.ndet, np.linspace(0, np.pi, na))
+    sp = Spectrum(wo.source, grid[:, 1], z["ea"], float(z["pixel_size"]))
+    meas = torch.from_numpy(wo.sinogram.reshape((1,) + wo.proj_shape).astype(np.float32)).cuda()
+    seen = []
+    solvers.white_barrier_stack(P, sp, meas, torch.from_numpy(z["x0"].astype(np.float32)).cuda()[None], ir_beta=ir_beta,
+                                add_stat_cb=seen.append, **p)
+    assert len(seen) == len(ref) > 3
+    for i in (0, 1, len(ref) - 1):
+        goal, regs, bfs = seen[i]
+        f_ref, x_ref, g_ref = ref[i]
+        assert isinstance(goal, StepStat) and set(regs) == {"ineq_reg"} and set(bfs) == {"conc_non_negative", "conc_less_than_one"}
+        assert goal.x.slices.tolist() == [0]
+        assert rel_l2(goal.x[0].cpu().numpy(), x_ref) < 1e-3 and abs(goal.func[0].item() - f_ref) < 1e-3 * abs(f_ref)
+        assert rel_l2(goal.grad[0].cpu().numpy(), g_ref) < 2e-3                      # the total gradient
+        xr = x_ref
+        assert rel_l2(regs["ineq_reg"].func[0].cpu().numpy(), ir_beta * np.abs(xr[0] * xr[1])) < 2e-3
+        assert rel_l2(bfs["conc_non_negative"].grad[0].cpu().numpy(), -1.0 / xr) < 2e-3
+        assert rel_l2(bfs["conc_less_than_one"].func[0].cpu().numpy(), -np.log(1 - xr)) < 2e-3
+
+
 def test_white_rec_stack_vs_oracle_iteration(golden):
     from whitomo_b200.projector import Projector, Spectrum
     from whitomo_b200 import solvers
@@ -151,10 +191,11 @@ def test_mar_barrier_least_squares_vs_reference_golden(golden):
     P = Projector(n, n, int(np.sqrt(2) * n + 1), np.linspace(0, np.pi, na))
     nb = int(z["n_biter"])
     x = solvers.barrier_least_squares(P, z["projections"].copy(), float(z["i0"]), float(z["bound"]), n_biter=nb)
-    assert x is not None and rel_l2(x.cpu().numpy(), z["ans"]) < 5e-3
+    # measured 2.3e-6 / 2.1e-5 (profiles/r2_test_margins.json)
+    assert x is not None and rel_l2(x.cpu().numpy(), z["ans"]) < TOL_REC
     x2 = solvers.barrier_least_squares(P, z["projections"].copy(), float(z["i0"]), float(z["bound"]), n_iter=100,
                                        n_biter=nb, t0=0.1, max_iter=1000, do_alpha_decay=True, with_sino_barrier=False)
-    assert rel_l2(x2.cpu().numpy(), z["ans_no_ineq"]) < 5e-3
+    assert rel_l2(x2.cpu().numpy(), z["ans_no_ineq"]) < TOL_REC
 
 
 def test_hough_barrier_class_on_device_closures(golden):
@@ -244,7 +285,7 @@ def test_white_projection_real_data_branch():
     wo = ow.WhiteOracle(np.array([2.0, 1.0]), 1e-5, np.array([[4000, 302.0], [300, 2000]]), grid, (w, w), geometry=g_geom)
     wo.sinogram = wp.sinogram
     assert abs(wp.func(c) - wo.func(c)) < 1e-4 * wo.func(c)
-    assert rel_l2(wp.grad(c), wo.grad(c)) < 5e-4
+    assert rel_l2(wp.grad(c), wo.grad(c)) < TOL_OP
 
 
 def test_example_script_reference_style_equals_fused():
@@ -380,6 +421,32 @@ def test_soft_inequality_least_squares_scipy_cg_over_the_drop_in():
     assert dev_c[0](xd) < dev_c[0](x0.astype(np.float64))
 
 
+def test_soft_inequality_least_squares_device_loop():
+    """solvers.ineq_linear_least_squares (teeth_recon/experiments.py:513-582 as a device loop: one FP + one BP per
+    iteration, no host synchronisation) on the B200 kernels against the same loop over the CPU oracle
+    (tests/test_soft_ineq_cpu.py ties that loop to the reference's closures and to scipy's fmin_cg)"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_projector import OracleProjector
+    from test_soft_ineq_cpu import _problem, reference_closures
+    from whitomo_b200.projector import Projector
+    from whitomo_b200 import solvers
+    g, ph, pr, i0, bound, alpha = _problem()
+    n = g.rows
+    ang = np.linspace(0, np.pi, g.nangles)
+    xc, hc = solvers.ineq_linear_least_squares(OracleProjector(n, n, g.ndet, ang), pr.copy(), i0, bound, alpha, n_iters=25)
+    xd, hd = solvers.ineq_linear_least_squares(Projector(n, n, g.ndet, ang), pr.copy(), i0, bound, alpha, n_iters=25)
+    assert np.allclose(hd.cpu().numpy()[:10], hc.numpy()[:10], rtol=1e-3)          # same descent, step by step
+    assert rel_l2(xd.cpu().numpy(), xc.numpy()) < 2e-2                             # CG amplifies fp32 rounding slowly
+    cost, grad = reference_closures(g, pr, i0, bound, alpha,
+                                    lambda x: oracle.fp(g, x.reshape(n, n)).flatten().astype(np.float64),
+                                    lambda x: oracle.bp(g, x.reshape(g.sino_shape)).flatten().astype(np.float64))
+    x0 = np.zeros(n * n)
+    assert np.linalg.norm(grad(xd.cpu().numpy().astype(np.float64).flatten())) < 0.05 * np.linalg.norm(grad(x0))
+    xl, hl = solvers.ineq_linear_least_squares(Projector(n, n, g.ndet, ang), pr.copy(), i0, bound, alpha, n_iters=150)
+    assert hl[-1].item() < 1e-4 * hl[0].item()
+
+
 def test_stack_job_checkpoint_and_resume(golden, tmp_path, monkeypatch):
     """every finished batch is written to the checkpoint directory; a restarted job loads what it finds (bit-identical)
     and recomputes only what is missing or was written for other data"""
@@ -426,3 +493,11 @@ def test_stack_job_checkpoint_and_resume(golden, tmp_path, monkeypatch):
     meas2[0] *= 1.01
     solvers.white_barrier_reconstruct(P, sp, meas2, x0, batch=3, checkpoint=ck, **p)
     assert calls == [3]                                                   # the batch holding the changed slice
+    # another assumed spectrum (same sizes) is another job; a statistics callback is not
+    calls.clear()
+    sp2 = Spectrum(z["source"] / np.sum(z["source"] * grid[:, 1]), grid[:, 1], 1.05 * z["ea"], float(z["pixel_size"]))
+    solvers.white_barrier_reconstruct(P, sp2, meas, x0, batch=3, checkpoint=ck, **p)
+    assert len(calls) == 3
+    calls.clear()
+    again, _ = solvers.white_barrier_reconstruct(P, sp, meas, x0, batch=3, checkpoint=ck, stat_cb=lambda st: None, **p)
+    assert torch.equal(again, ref) and calls == [3]       # same job key: only the batch the meas2 run overwrote is redone

@@ -667,6 +667,11 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
     if (nslices <= 0) return invalid("wt_white_fp: nslices must be positive");
     if (angle_begin < 0 || angle_end > g->nangles || angle_begin > angle_end) return invalid("wt_white_fp: bad angle range");
     const int K = s->K, n = nslices * K;
+    {
+        int dev = -1;
+        WT_CUDA(cudaGetDevice(&dev));
+        if (dev != s->device) return invalid("wt_white_fp: the spectrum was created on another device than the current one");
+    }
     if (ws_bytes < wt_workspace_bytes(g, n)) { g_err = "wt_white_fp: workspace too small"; return WT_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)g->nangles * g->ndet;

@@ -87,6 +87,7 @@ struct FpEpiWhite {
         // costs no shared-memory wavefronts -- K + 1 broadcast LDS per bin were 3.5 % of this LSU-bound kernel's
         // wavefronts (a float4 row per bin was worse: a broadcast LDS.128 still takes four).  Larger tables, or more
         // live spectra than slots, use the idle staging buffers, or stay in global memory.
+        if (partial && pass > 0) __syncthreads();   // the previous pass may still be summing `red` (CTA-uniform condition)
         const int ntab = (K + 1) * E;
         const bool in_const = cslot >= 0;
         const bool in_smem = !in_const && ntab * (int)sizeof(float) <= FP_STAGES * FP_LB * FP_W * (int)sizeof(float);

@@ -41,18 +41,23 @@ class Spectrum(object):
     """Device tables of the polychromatic model (constructor state of WhiteProjection,
     src/white_projection.py:23-73).  ``source`` must already be normalised by its integral."""
 
-    def __init__(self, source, widths, absorptions, pixel_size):
+    def __init__(self, source, widths, absorptions, pixel_size, device=None):
+        """``device``: the GPU the tables live on (default: the current one); use the Projector's device."""
         _require_cuda()
         self.lib = _capi.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         source = np.ascontiguousarray(source, dtype=np.float64)
         widths = np.ascontiguousarray(widths, dtype=np.float64)
         absorptions = np.ascontiguousarray(absorptions, dtype=np.float64)
         self.K, self.E = absorptions.shape
         assert source.shape == (self.E,) and widths.shape == (self.E,)
+        # host copies: what a checkpoint of a reconstruction depends on (solvers._checkpoint_key)
+        self.source, self.widths, self.absorptions, self.pixel_size = source, widths, absorptions, float(pixel_size)
         h = ctypes.c_void_p()
         dp = ctypes.POINTER(ctypes.c_double)
-        _capi.check(self.lib.wt_spectrum_create(self.K, self.E, source.ctypes.data_as(dp), widths.ctypes.data_as(dp),
-                                                absorptions.ctypes.data_as(dp), float(pixel_size), ctypes.byref(h)))
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.wt_spectrum_create(self.K, self.E, source.ctypes.data_as(dp), widths.ctypes.data_as(dp),
+                                                    absorptions.ctypes.data_as(dp), float(pixel_size), ctypes.byref(h)))
         self.handle = h
 
     def __del__(self):
@@ -232,6 +237,8 @@ class Projector(object):
                  angle_range=None):
         """Fused white-beam forward model + residual (wt_white_fp).  conc (S, K, rows, cols) or (K, rows, cols).
         Returns (intensity (S,A,D) | None, qmu (S,K,A,D) | None, loss (S,) float64 | None)."""
+        if spectrum.device != self.device:
+            raise ValueError("the Spectrum lives on %s, the Projector on %s" % (spectrum.device, self.device))
         c, lead = self._as_images(conc, self.vol_shape)
         K = spectrum.K
         if c.shape[0] % K:

@@ -30,7 +30,7 @@ def _as_stack(x, K):
 
 def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1, t_step=0.5, alpha=1.0,
                         beta_reg=1.0, ir_beta=0.05, max_iter=5000, do_alpha_decay=True, min_delta_loss=1e-3,
-                        n_steps_without_progress=15, stat_cb=None, max_total_iters=None, compact=True):
+                        n_steps_without_progress=15, add_stat_cb=None, max_total_iters=None, compact=True, stat_cb=None):
     """Log-barrier reconstruction of element concentrations 0 <= c <= 1 with the 0.05*|c0 c1| regulariser.
 
     Defaults are the reference's run (src/barrier_method_gogo.py:184-192).  ``meas`` (S, A, D) intensities,
@@ -39,6 +39,14 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
     Per inner iteration and slice: one fused white-beam FP (K projections), K BP, one K3 launch.
     The loss of barrier_method's early-stop test at the new point is f(x') + penalty(x'); f(x') is the by-product
     of the FP that the next iteration's gradient needs anyway, so no projection is spent on statistics.
+    ``add_stat_cb`` (alias ``stat_cb``) receives what the reference's callback receives (src/barrier_method.py:182-199):
+    the tuple ``(goal_stat, reg_stats, bf_stats)`` of ``StepStat(x, func, grad)`` -- goal: f(x) and the TOTAL gradient
+    (the reference accumulates into the goal gradient in place); ``reg_stats['ineq_reg']``: the
+    0.05 |c0 c1| term and its gradient; ``bf_stats['conc_non_negative' | 'conc_less_than_one']``: phi and grad phi of
+    the two box barriers -- as device tensors with a leading axis over the slices of the working set (their stack
+    indices are ``goal_stat.x.slices``), at the reference's cadence (every inner iteration while the outer iteration
+    index is < 30 or a multiple of 10, B6).  f(x) comes from the projector's epilogue; the other statistics cost a few
+    element-wise passes, spent only when a callback is installed.
     Early stop is per slice (each slice is its own barrier_method problem).  With ``compact`` the slices that left
     a barrier level early are taken out of the working set until the next level, so no FP/BP is spent on them
     (the working set never drops below 3 images, which keeps every slice on the batched kernels and its result
@@ -49,6 +57,7 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
     S = x.shape[0]
     meas = meas.reshape((S,) + proj.sino_shape).to(torch.float32).contiguous()
     dev = x.device
+    add_stat_cb = add_stat_cb if add_stat_cb is not None else stat_cb
     if not bool(((x > 0) & (x < 1)).all()):         # src/barrier_method.py:128-152 (box projection, then re-check)
         x.clamp_(0, 1)
         if not bool(((x >= 0) & (x <= 1)).all()):
@@ -70,8 +79,8 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
         for i_iter in range(n_iter):
             n_w = xw.shape[0]
             g = proj.bp(qw.reshape((n_w * K,) + proj.sino_shape), scale=-1.0)
-            if stat_cb is not None:
-                stat_cb(dict(biter=i_biter, iter=i_iter, t=t, alpha=alpha, x=xw, slices=idx, func=fw, grad=g))
+            if add_stat_cb is not None and (i_biter % 10 == 0 or i_biter < 30):
+                add_stat_cb(_white_barrier_stats(xw, idx, fw, g.reshape(xw.shape), beta_reg, ir_beta, t))
             pen = proj.barrier_update(xw, g, alpha, beta_reg, t, reg_w=ir_beta, active=active,
                                       want_penalty=n_steps_without_progress is not None)
             _, qw, fw = proj.white_fp(spectrum, xw, meas=mw, want_intensity=False)
@@ -111,6 +120,32 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
         if done:
             break
     return x, dict(iters=total, loss=f_loss, trace=trace, slice_iters=slice_iters)
+
+
+class _SnapShot(torch.Tensor):
+    """a tensor that remembers which slices of the stack it holds (StepStat.x of the fused loops)"""
+
+
+def _white_barrier_stats(xw, idx, f_loss, g, beta_reg, ir_beta, t):
+    """the reference's (goal_stat, reg_stats, bf_stats) for the gogo problem (src/barrier_method.py:182-199 with the
+    tuples of src/barrier_method_gogo.py:79-94), batched over the working set"""
+    from .barrier_method import StepStat
+    snap = xw.clone().as_subclass(_SnapShot)
+    snap.slices = idx.clone()
+    K = xw.shape[1]
+    inf = torch.full_like(xw, float("inf"))
+    reg_val = ir_beta * (xw[:, 0] * xw[:, 1]).abs() if K == 2 else torch.zeros_like(xw[:, 0])
+    reg_grad = torch.zeros_like(xw)
+    if K == 2:
+        sgn = torch.sign(xw[:, 0] * xw[:, 1])
+        reg_grad[:, 0], reg_grad[:, 1] = ir_beta * xw[:, 1] * sgn, ir_beta * xw[:, 0] * sgn
+    phi_lo = torch.where(xw > 0, -torch.log(xw), inf)              # f = -x:     phi = -log(x),   grad phi = -1/x
+    phi_hi = torch.where(xw < 1, -torch.log1p(-xw), inf)           # f = x - 1:  phi = -log(1-x), grad phi = 1/(1-x)
+    g_lo, g_hi = -1.0 / xw, 1.0 / (1.0 - xw)
+    total = g + beta_reg * reg_grad + beta_reg * t * (g_lo + g_hi)
+    return (StepStat(snap, f_loss.clone(), total),
+            {"ineq_reg": StepStat(snap, reg_val, reg_grad)},
+            {"conc_non_negative": StepStat(snap, phi_lo, g_lo), "conc_less_than_one": StepStat(snap, phi_hi, g_hi)})
 
 
 def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=1e-2, clip_concentrations=True,
@@ -251,10 +286,15 @@ def _checkpoint_key(proj, spectrum, meas_host, x0_host, params):
     import hashlib
     import json
     h = hashlib.sha256()
-    h.update(json.dumps({"rows": proj.rows, "cols": proj.cols, "ndet": proj.ndet, "K": spectrum.K, "E": spectrum.E,
-                         "params": {k: repr(v) for k, v in sorted(params.items())},
+    # solver parameters that shape the result; callables (stat_cb) carry no data and their repr an address
+    data_params = {k: repr(v) for k, v in sorted(params.items()) if not callable(v)}
+    h.update(json.dumps({"rows": proj.rows, "cols": proj.cols, "ndet": proj.ndet, "det_width": proj.det_width,
+                         "positions": getattr(proj, "positions", None), "K": spectrum.K, "E": spectrum.E,
+                         "pixel_size": repr(getattr(spectrum, "pixel_size", None)), "params": data_params,
                          "meas": list(meas_host.shape), "x0": list(x0_host.shape)}, sort_keys=True).encode())
     h.update(np.ascontiguousarray(proj.angles).tobytes())
+    for tab in ("source", "widths", "absorptions"):          # the assumed spectrum: another one is another job
+        h.update(np.ascontiguousarray(getattr(spectrum, tab, np.zeros(0))).tobytes())
     return h.hexdigest()[:16]
 
 
@@ -395,3 +435,61 @@ def mask_linear_least_squares(proj, pr, i0, bound, n_iters=200, x0=None):
         d = s + (gamma_new / gamma).float() * d
         gamma = gamma_new
     return x, costs
+
+
+def ineq_linear_least_squares(proj, pr, i0, bound, alpha, n_iters=200, x0=None, newton_steps=6):
+    """Soft-inequality least squares of teeth_recon/experiments.py:513-582 as a device loop.
+
+    Good rays pull W x towards the measured ray sums b; photon-starved (metal) rays, whose true ray sum is only known to
+    exceed b_m = log(i0 / bound), are penalised one-sidedly: d = W x - b, d[m & (d > 0)] = 0, d[m] *= alpha.  The
+    reference hands ``cost`` and ``grad = 2 W^T(d_good / n_good', alpha d_bad / n_bad)`` to scipy.optimize.fmin_cg (that
+    path keeps working unchanged over the drop-in gpu_fp / gpu_bp, one H2D + D2H per projector call).  Its ``grad`` is the
+    gradient of   G(x) = sum_r w_r rho_r(W x - b)_r^2,   w = 1 on good rays (1 / n_good on the two rays the reference's
+    literal ``d[1 - m]`` index hits), alpha / n_bad on starved rays, rho one-sided there -- which is what fmin_cg drives
+    to a stationary point.  This loop minimises G with Polak-Ribiere+ non-linear CG: G is piecewise quadratic along a
+    line and W d is known after ONE forward projection of the direction, so the line search is a few Newton steps on
+    sinogram-sized arrays without touching the projector -- one FP and one BP per iteration, every dot product on the
+    device, no host synchronisation inside the loop.  Iterates differ from scipy's; stationary points agree.
+    Returns (x, G per iteration as a float64 tensor)."""
+    dev = proj.device
+    p = torch.as_tensor(np.asarray(pr) if not isinstance(pr, torch.Tensor) else pr).to(dev, dtype=torch.float32).clone()
+    r, m = ray_transform_from_projection(p.reshape(proj.sino_shape), bound, i0)
+    b = torch.where(m, torch.full_like(r, math.log(i0) - math.log(bound)), r)
+    n_bad = int(m.sum().item())
+    n_good = m.numel() - n_bad
+    w = torch.where(m, torch.full_like(r, float(alpha) / max(n_bad, 1)), torch.ones_like(r))
+    w.view(-1)[:2] /= float(n_good)                  # ``d[1 - m] /= n_good`` indexes elements 0 and 1 (m is a 0/1 array)
+
+    def resid(px):
+        d = px - b
+        return torch.where(m & (d > 0), torch.zeros_like(d), d)
+
+    x = torch.zeros(proj.vol_shape, dtype=torch.float32, device=dev) if x0 is None else x0.to(dev).float().clone()
+    px = proj.fp(x)
+    d = resid(px)
+    g = 2.0 * proj.bp(w * d)
+    dirn = -g
+    gg = torch.sum(g.double() * g.double())
+    hist = []
+    for _ in range(n_iters):
+        hist.append(torch.sum(w.double() * d.double() ** 2))
+        pd = proj.fp(dirn)
+        step = torch.zeros((), dtype=torch.float64, device=dev)
+        for _ in range(newton_steps):                # phi(s) = G(x + s dirn) is convex and piecewise quadratic
+            cur = px + step.float() * pd - b
+            act = ~(m & (cur > 0))
+            dd = torch.where(act, cur, torch.zeros_like(cur))
+            g1 = torch.sum((w * dd).double() * pd.double())
+            g2 = torch.sum((w * act).double() * pd.double() ** 2)
+            step = step - torch.where(g2 > 0, g1 / g2, torch.zeros_like(g1))
+        x += step.float() * dirn
+        px += step.float() * pd
+        d = resid(px)
+        g_new = 2.0 * proj.bp(w * d)
+        gg_new = torch.sum(g_new.double() * g_new.double())
+        beta = torch.clamp((gg_new - torch.sum(g_new.double() * g.double())) / gg, min=0.0)     # Polak-Ribiere+
+        beta = torch.where(torch.isfinite(beta), beta, torch.zeros_like(beta))
+        dirn = -g_new + beta.float() * dirn
+        g, gg = g_new, gg_new
+    hist.append(torch.sum(w.double() * d.double() ** 2))
+    return x, torch.stack(hist)
