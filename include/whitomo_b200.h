@@ -169,6 +169,26 @@ typedef struct {
     unsigned elem_mask;
 } wt_update_params;
 
+/* One whole inner iteration of the white-beam loops in three launches: K2 (backprojection of the packed q*mu of the
+ * previous forward model, its epilogue taking the wt_barrier_update step on x and refreshing the forward projector's
+ * packed copies of x), K1 (white-beam forward model at the new x, its epilogue writing q*mu straight into K2's packed
+ * layout and the partial sums of the data term), one reduction.  Replaces, per inner iteration, the same reference
+ * code as wt_white_fp + wt_bp(scale = -1) + wt_barrier_update together (src/barrier_method.py:163-229 with
+ * src/white_projection.py:116-127; src/white_rec.py:199-244) -- without the gradient array, the q*mu array and the two
+ * re-packing passes those separate calls exchange.  n_elements K <= 2; not for mirror-paired calls.
+ *   flags & WT_STEP_INIT: (re)start -- pack x, run the forward model only; loss = f(x), no step, penalty untouched.
+ *   otherwise:            x <- step(x, -W^T(q mu)) with *prm (see wt_barrier_update), then the forward model at the new
+ *                         x;  loss (nslices, float64, optional) = f(x_new),  penalty (optional) = the wt_barrier_update
+ *                         penalty at x_new.
+ * State (the packed x and q*mu) lives in `ws` between calls: the same `ws` (>= wt_step_workspace_bytes) must be passed,
+ * untouched, from a WT_STEP_INIT call on; any other use of it, a change of nslices, or writing x from outside
+ * requires a new WT_STEP_INIT. */
+#define WT_STEP_INIT 1
+size_t wt_step_workspace_bytes(const wt_geom *g, int nslices, int n_elements);
+int wt_white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, const float *meas,
+                          const wt_update_params *prm, const unsigned char *active, double *loss, double *penalty,
+                          int nslices, int flags, void *ws, size_t ws_bytes, void *stream);
+
 int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix,
                       const wt_update_params *prm, const unsigned char *active, double *penalty, void *ws,
                       size_t ws_bytes, void *stream);

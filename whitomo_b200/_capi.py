@@ -35,6 +35,9 @@ SIGNATURES = {
     "wt_spectrum_destroy": (None, [c_void_p]),
     "wt_white_fp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_size_t, c_void_p]),
+    "wt_step_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "wt_white_barrier_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p, c_size_t, c_void_p]),
     "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
 }
@@ -49,6 +52,7 @@ class UpdateParams(ctypes.Structure):
 
 UPD_STEP_CLIP, UPD_STEP_ONLY, UPD_CLIP_ONLY = 0, 1, 2
 POS_ASTRA, POS_EXACT = 0, 1
+STEP_INIT = 1
 
 _lib = None
 

@@ -69,9 +69,10 @@ static inline bool use_mirror(const wt_geom *g, int n) {
 static inline int packed_images(const wt_geom *g, int n) { return use_mirror(g, n) ? 2 * n : chunk_of(n).v * chunk_of(n).groups; }
 
 // returns the number of per-image partial-sum slots the epilogue wrote (CTAs x passes), or a negative error
+// packed_in: vn / vt already hold the packed copies of the volume (written by a previous kernel's epilogue)
 template <class Epi>
 static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_end, float *vn, float *vt,
-                  const Epi &epi_proto, cudaStream_t st) {
+                  const Epi &epi_proto, cudaStream_t st, bool packed_in = false) {
     FpParams p;
     p.vn = vn; p.vt = vt; p.ang = g->d_fp;
     p.tiles = (const FpTile *)g->d_tiles; p.ntiles = g->ntiles;
@@ -109,12 +110,12 @@ static int run_fp(const wt_geom *g, const float *vol, int n, int a_begin, int a_
     if (n % Epi::kMult) return invalid("run_fp: image count is not a multiple of the element count");
     const Chunk c = chunk_of(n);
     switch (c.v) {
-    case 4: launch_pack_vol<4>(vol, vn, vt, p.R, p.C, c.groups, n, copies, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
+    case 4: if (!packed_in) launch_pack_vol<4>(vol, vn, vt, p.R, p.C, c.groups, n, copies, st); WT_CUDA((launch_fp<4, Epi>(p, epi, c.groups, st))); break;
     case 2:
-        if constexpr (2 % Epi::kMult == 0) { launch_pack_vol<2>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<2, Epi>(p, epi, 1, st))); }
+        if constexpr (2 % Epi::kMult == 0) { if (!packed_in) launch_pack_vol<2>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<2, Epi>(p, epi, 1, st))); }
         break;
     default:
-        if constexpr (Epi::kMult == 1) { launch_pack_vol<1>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<1, Epi>(p, epi, 1, st))); }
+        if constexpr (Epi::kMult == 1) { if (!packed_in) launch_pack_vol<1>(vol, vn, vt, p.R, p.C, 1, n, copies, st); WT_CUDA((launch_fp<1, Epi>(p, epi, 1, st))); }
         break;
     }
     WT_CUDA(cudaGetLastError());
@@ -141,16 +142,25 @@ static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a
         return invalid("run_bp: bad row range (row_begin must be a multiple of the tile height)");
     if (p.row_begin == p.row_end) return WT_OK;
     if (mirror) {
-        if (n == 1) { if (!packed) launch_pack_sino<2, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
-        else { if (!packed) launch_pack_sino<4, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
-        WT_CUDA(cudaGetLastError());
-        return WT_OK;
+        if constexpr (!Epi::kHasSums) {
+            if (n == 1) { if (!packed) launch_pack_sino<2, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi, true>(p, epi, 1, st))); }
+            else { if (!packed) launch_pack_sino<4, true>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi, true>(p, epi, 1, st))); }
+            WT_CUDA(cudaGetLastError());
+            return WT_OK;
+        } else {
+            return invalid("run_bp: this epilogue is not mirror-paired");
+        }
     }
+    if (n % Epi::kMult) return invalid("run_bp: image count is not a multiple of the element count");
     const Chunk c = chunk_of(n);
     switch (c.v) {
     case 4: if (!packed) launch_pack_sino<4>(sino, sp, g, c.groups, n, a_begin, a_end, st); WT_CUDA((launch_bp<4, Epi>(p, epi, c.groups, st))); break;
-    case 2: if (!packed) launch_pack_sino<2>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); break;
-    default: if (!packed) launch_pack_sino<1>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); break;
+    case 2:
+        if constexpr (2 % Epi::kMult == 0) { if (!packed) launch_pack_sino<2>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<2, Epi>(p, epi, 1, st))); }
+        break;
+    default:
+        if constexpr (Epi::kMult == 1) { if (!packed) launch_pack_sino<1>(sino, sp, g, 1, n, a_begin, a_end, st); WT_CUDA((launch_bp<1, Epi>(p, epi, 1, st))); }
+        break;
     }
     WT_CUDA(cudaGetLastError());
     return WT_OK;
@@ -160,6 +170,10 @@ static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a
 struct HFpStore : FpEpiStore { static constexpr int kMult = 1; };
 struct HFpSirt : FpEpiSirtResidual { static constexpr int kMult = 1; };
 struct HFpMar : FpEpiMar { static constexpr int kMult = 1; };
+static int bp_slots(const wt_geom *g) {      // partial-sum slots per slice of an epilogue with sums: (tile, consumer warp)
+    const int th = bp_tile_height(g->rows, g->cols);
+    return ((g->cols + BP_TW - 1) / BP_TW) * ((g->rows + th - 1) / th) * (BP_THREADS / 32);
+}
 template <int K> struct HFpWhite : FpEpiWhite<K> { static constexpr int kMult = K; };
 typedef BpEpiStore HBpStore;
 typedef BpEpiSirtUpdate HBpSirt;
@@ -610,12 +624,23 @@ int wt_sirt(const wt_geom *g, const float *sino, float *vol, int nimages, int n_
     rc = run_bp(g, resid, 1, 0, g->nangles, sp, bs, st);
     if (rc) return rc;
     WT_CUDA(cudaMemsetAsync(vol, 0, sizeof(float) * nimages * img, st));
+    // Two launches per iteration: K1's epilogue writes the weighted residual straight into K2's packed sinogram layout,
+    // K2's epilogue updates the volume and refreshes K1's packed copies (the zero padding of the packed buffers is
+    // written once, here; x0 = 0 is all zeros).  Mirror-paired calls (WT_POS_EXACT, one or two large images) keep the
+    // pack kernels: their packed copies also hold the point reflections.
+    const bool fused = !use_mirror(g, nimages);
+    if (fused) {
+        WT_CUDA(cudaMemsetAsync(vn, 0, sizeof(float) * vn_floats(g, npack), st));
+        WT_CUDA(cudaMemsetAsync(vt, 0, sizeof(float) * vt_floats(g, npack), st));
+        WT_CUDA(cudaMemsetAsync(sp, 0, sizeof(float) * (size_t)npack * g->nangles * g->sino_pitch, st));
+    }
     for (int it = 0; it < n_iters; ++it) {
-        HFpSirt fe; fe.meas = sino; fe.raysum = raysum; fe.out = resid;
-        rc = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, fe, st);
+        HFpSirt fe; fe.meas = sino; fe.raysum = raysum; fe.out = fused ? nullptr : resid;
+        fe.sp = fused ? sp : nullptr; fe.padl = g->sino_padl; fe.pitch = g->sino_pitch;
+        rc = run_fp(g, vol, nimages, 0, g->nangles, vn, vt, fe, st, fused);
         if (rc < 0) return rc;
-        HBpSirt be; be.vol = vol; be.pixsum = pixsum;
-        rc = run_bp(g, resid, nimages, 0, g->nangles, sp, be, st);
+        HBpSirt be; be.vol = vol; be.pixsum = pixsum; be.vn = fused ? vn : nullptr; be.vt = fused ? vt : nullptr;
+        rc = run_bp(g, resid, nimages, 0, g->nangles, sp, be, st, 0, -1, fused);
         if (rc) return rc;
     }
     return WT_OK;
@@ -688,11 +713,11 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
         int rc;
         if (K == 1) {
             HFpWhite<1> e; e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = intensity; e.qmu = qmu;
-            e.partial = loss ? partial : nullptr;
+            e.partial = loss ? partial : nullptr; e.sp = nullptr; e.padl = 0; e.pitch = 0;
             rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         } else {
             HFpWhite<2> e; e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = intensity; e.qmu = qmu;
-            e.partial = loss ? partial : nullptr;
+            e.partial = loss ? partial : nullptr; e.sp = nullptr; e.padl = 0; e.pitch = 0;
             rc = run_fp(g, conc, n, angle_begin, angle_end, vn, vt, e, st);
         }
         if (rc < 0) return rc;
@@ -712,6 +737,81 @@ int wt_white_fp(const wt_geom *g, const wt_spectrum *s, const float *conc, const
         WT_CUDA(cudaGetLastError());
     }
     return WT_OK;
+}
+
+size_t wt_step_workspace_bytes(const wt_geom *g, int nslices, int n_elements) {
+    if (!g || nslices <= 0 || n_elements <= 0) return 0;
+    return wt_workspace_bytes(g, nslices * n_elements) + align_up((size_t)nslices * bp_slots(g) * sizeof(double), 256) + 1024;
+}
+
+}  // extern "C"
+
+template <int K>
+static int white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, const float *meas, const wt_update_params *prm,
+                              const unsigned char *active, double *loss, double *penalty, int nslices, int flags, void *ws,
+                              size_t ws_bytes, cudaStream_t st) {
+    const int n = nslices * K;
+    Carver cv(ws, ws_bytes);
+    const int npack = packed_images(g, n);
+    float *vn = cv.take<float>(vn_floats(g, npack));
+    float *vt = cv.take<float>(vt_floats(g, npack));
+    float *sp = cv.take<float>((size_t)npack * g->nangles * g->sino_pitch);
+    float *lpart = cv.take<float>((size_t)3 * npack * fp_blocks(g));
+    cv.take<double>((size_t)n * UPD_BLOCKS_PER_SLICE);
+    const int nslots = bp_slots(g);
+    double *ppart = cv.take<double>((size_t)nslices * nslots);
+    if (!cv.ok()) { g_err = "wt_white_barrier_step: workspace too small (wt_step_workspace_bytes)"; return WT_ERR_WORKSPACE; }
+    const Chunk c = chunk_of(n);
+    if (flags & WT_STEP_INIT) {
+        // packed copies of x (with their zero padding) and an all-zero packed sinogram buffer (K1 only writes detectors
+        // [0, ndet) of every row); no update: the forward model below then produces q*mu and f(x) of the start point
+        switch (c.v) {
+        case 4: launch_pack_vol<4>(x, vn, vt, g->rows, g->cols, c.groups, n, 3, st); break;
+        case 2: launch_pack_vol<2>(x, vn, vt, g->rows, g->cols, 1, n, 3, st); break;
+        default: launch_pack_vol<1>(x, vn, vt, g->rows, g->cols, 1, n, 3, st); break;
+        }
+        WT_CUDA(cudaMemsetAsync(sp, 0, sizeof(float) * (size_t)npack * g->nangles * g->sino_pitch, st));
+    } else {
+        // K2 over the packed q*mu of the previous forward model; its epilogue takes the step and refreshes VN / VT
+        BpEpiBarrierUpdate<K> be;
+        be.x = x; be.prm = *prm; be.active = active; be.partial = penalty ? ppart : nullptr; be.vn = vn; be.vt = vt; be.gscale = -1.0f;
+        const int rc = run_bp(g, nullptr, n, 0, g->nangles, sp, be, st, 0, -1, true);
+        if (rc) return rc;
+    }
+    HFpWhite<K> e;
+    e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = nullptr; e.qmu = nullptr;
+    e.partial = loss ? lpart : nullptr; e.sp = sp; e.padl = g->sino_padl; e.pitch = g->sino_pitch;
+    const int nb = run_fp(g, x, n, 0, g->nangles, vn, vt, e, st, true);
+    if (nb < 0) return nb;
+    if (loss || (penalty && !(flags & WT_STEP_INIT))) {
+        reduce_step_kernel<<<dim3(nslices, 2), 32, 0, st>>>(lpart, nb, loss, (flags & WT_STEP_INIT) ? nullptr : ppart, nslots,
+                                                             (flags & WT_STEP_INIT) ? nullptr : penalty);
+        WT_CUDA(cudaGetLastError());
+    }
+    return WT_OK;
+}
+
+extern "C" {
+
+int wt_white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, const float *meas, const wt_update_params *prm,
+                          const unsigned char *active, double *loss, double *penalty, int nslices, int flags, void *ws,
+                          size_t ws_bytes, void *stream) {
+    if (!g || !s || !x || !ws) return invalid("wt_white_barrier_step: null pointer");
+    if (!(flags & WT_STEP_INIT) && !prm) return invalid("wt_white_barrier_step: update parameters required");
+    if (nslices <= 0) return invalid("wt_white_barrier_step: nslices must be positive");
+    const int K = s->K;
+    if (K != 1 && K != 2) { g_err = "wt_white_barrier_step: fused iteration needs K <= 2 (use wt_white_fp / wt_bp / wt_barrier_update)"; return WT_ERR_UNSUPPORTED; }
+    if (use_mirror(g, nslices * K)) { g_err = "wt_white_barrier_step: not available for mirror-paired calls (WT_POS_EXACT, <= 2 large images)"; return WT_ERR_UNSUPPORTED; }
+    if (prm && prm->reg_w != 0.0f && K != 2) return invalid("wt_white_barrier_step: the |c0 c1| regulariser needs K == 2");
+    if (prm && (prm->mode < 0 || prm->mode > 2)) return invalid("wt_white_barrier_step: bad mode");
+    {
+        int dev = -1;
+        WT_CUDA(cudaGetDevice(&dev));
+        if (dev != s->device) return invalid("wt_white_barrier_step: the spectrum was created on another device than the current one");
+    }
+    if (ws_bytes < wt_step_workspace_bytes(g, nslices, K)) { g_err = "wt_white_barrier_step: workspace too small"; return WT_ERR_WORKSPACE; }
+    if (K == 1) return white_barrier_step<1>(g, s, x, meas, prm, active, loss, penalty, nslices, flags, ws, ws_bytes, (cudaStream_t)stream);
+    return white_barrier_step<2>(g, s, x, meas, prm, active, loss, penalty, nslices, flags, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix, const wt_update_params *prm,

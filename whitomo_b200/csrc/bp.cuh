@@ -63,6 +63,8 @@ struct BpParams {
 
 // plain store: vol (n, R, C)
 struct BpEpiStore {
+    static constexpr bool kHasSums = false;
+    static constexpr int kMult = 1;      // images per problem: a group of V interleaved images must hold whole problems
     float *vol;
     float scale;
     template <int V>
@@ -109,6 +111,11 @@ struct BpSmem {
 //   BP_F_FOUR    rays less than a position apart on the pixel line (the warp compresses them): up to three rays reach a
 //                pixel, so four candidate taps are weighted.  Every pixel is located on its own (the generic path).
 constexpr int BP_F_GENERIC = 1, BP_F_MIN = 2, BP_F_FOUR = 4, BP_F_KINK = 8;
+
+// Epilogues with kHasSums accumulate up to BP_MAX_SUMS per-thread sums (operator() gets a float* to them); the kernel
+// reduces them over the warp and hands them to epi.finish<W>(p, g, slot, nslots, sums): slot = (tile, warp), so the
+// partial sums are written in a fixed place and reduced in a fixed order by a later kernel (deterministic).
+constexpr int BP_MAX_SUMS = 4;
 
 // Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
 // MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
@@ -430,6 +437,9 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s
     }
 
+    float sums[BP_MAX_SUMS];
+#pragma unroll
+    for (int q = 0; q < BP_MAX_SUMS; ++q) sums[q] = 0.0f;
 #pragma unroll
     for (int r = 0; r < BP_RPT; ++r) {
         const int row = row0 + bp_row_of(warp, r);
@@ -438,6 +448,7 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             const int col = col0 + lane + 32 * c;
             if (row < p.row_end && col < p.C) {
                 if constexpr (MIRROR) {
+                    static_assert(!Epi::kHasSums, "epilogues with sums are not mirror-paired");
                     constexpr int W = V / 2;
                     float direct[W], mirrored[W];
 #pragma unroll
@@ -445,11 +456,20 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
                     epi.template operator()<W>(p, g, row, col, direct);
                     const int mr = p.R - 1 - row;     // the middle row of an odd-height image is its own mirror row
                     if (mr != row) epi.template operator()<W>(p, g, mr, p.C - 1 - col, mirrored);
+                } else if constexpr (Epi::kHasSums) {
+                    epi.template operator()<V>(p, g, row, col, acc[r][c], sums);
                 } else {
                     epi.template operator()<V>(p, g, row, col, acc[r][c]);
                 }
             }
         }
+    }
+    if constexpr (Epi::kHasSums && !MIRROR) {
+#pragma unroll
+        for (int q = 0; q < BP_MAX_SUMS; ++q) sums[q] = warp_sum(sums[q]);
+        if (lane == 0)
+            epi.template finish<V>(p, g, (int)((blockIdx.y * gridDim.x + blockIdx.x) * (BP_THREADS / 32) + warp),
+                                   (int)(gridDim.x * gridDim.y * (BP_THREADS / 32)), sums);
     }
 }
 

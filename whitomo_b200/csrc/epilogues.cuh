@@ -10,36 +10,54 @@ namespace wt {
 struct FpEpiSirtResidual {
     const float *meas;    // (n, A, D)
     const float *raysum;  // (A, D)
-    float *out;           // (n, A, D)
+    float *out;           // (n, A, D), or null when the residual goes straight into K2's packed layout:
+    float *sp;            // (G, A, pitch, V) with `padl` zero detectors in front (bp.cuh: pack_sino_kernel), or null
+    int padl, pitch;
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
-                                               const float (&val)[V], float *, int, int) const {
+                                               const float (&val)[V], float *, int pass, int) const {
         if (!valid) return;
         const size_t plane = (size_t)p.A * p.D, r = (size_t)a * p.D + d;
         const float rs = __ldg(raysum + r);
+        float res[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            res[i] = 0.0f;
             if (g * V + i >= p.nimg) continue;       // padding component of the last group
             const size_t o = ((size_t)g * V + i) * plane + r;
             const float diff = __ldg(meas + o) - val[i];
-            out[o] = rs > 0.000001f ? diff / rs : 0.0f;
+            res[i] = rs > 0.000001f ? diff / rs : 0.0f;
+            if (out) out[o] = res[i];
         }
+        if (sp && pass == 0)    // (packed output is never combined with mirror pairing)
+            reinterpret_cast<typename VecOf<V>::T *>(sp)[((size_t)g * p.A + a) * pitch + padl + d] = pack<V>(res);
     }
 };
 
 struct BpEpiSirtUpdate {
+    static constexpr bool kHasSums = false;
+    static constexpr int kMult = 1;
     float *vol;           // (n, R, C), updated in place
     const float *pixsum;  // (R, C)
+    float *vn, *vt;       // K1's packed copies of the volume, refreshed in place (fp.cuh: pack_vol_kernel), or null
     template <int V>
     __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col,
                                                const float (&val)[V]) const {
         const size_t img = (size_t)p.R * p.C, px = (size_t)row * p.C + col;
         const float cs = __ldg(pixsum + px);
+        float nv[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            nv[i] = 0.0f;
             if (g * V + i >= p.nimg) continue;       // padding component of the last group
             const size_t o = ((size_t)g * V + i) * img + px;
-            vol[o] += cs > 0.000001f ? val[i] / cs : 0.0f;
+            nv[i] = vol[o] + (cs > 0.000001f ? val[i] / cs : 0.0f);
+            vol[o] = nv[i];
+        }
+        if (vn) {
+            typedef typename VecOf<V>::T VecT;
+            reinterpret_cast<VecT *>(vn)[((size_t)g * p.R + row) * fp_pitch(p.C) + VPAD + col] = pack<V>(nv);
+            reinterpret_cast<VecT *>(vt)[((size_t)g * p.C + col) * fp_pitch(p.R) + VPAD + row] = pack<V>(nv);
         }
     }
 };
@@ -72,6 +90,8 @@ struct FpEpiWhite {
     float *inten;       // (S, A, D) or null
     float *qmu;         // (S, K, A, D) or null
     float *partial;     // (S, nblocks) per-CTA sums of q^2, or null
+    float *sp;          // q*mu in K2's packed layout (G, A, pitch, V), `padl` zero detectors in front, or null
+    int padl, pitch;
     template <int V>
     __device__ __forceinline__ void operator()(const FpParams &p, int g, int a, int d, bool valid,
                                                const float (&val)[V], float *scratch, int pass, int npass) const {
@@ -131,6 +151,9 @@ struct FpEpiWhite {
             if (in_const) bins([&](int i) { return c_spectrum_tab[cbase + i]; });
             else bins([&](int i) { return tb[i]; });
         }
+        float packed[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) packed[i] = 0.0f;
 #pragma unroll
         for (int sl = 0; sl < SPG; ++sl) {
             const size_t slice = (size_t)g * SPG + sl;
@@ -139,9 +162,10 @@ struct FpEpiWhite {
             if (valid && real) {
                 const float q = (meas ? __ldg(meas + slice * plane + r) : 0.0f) - I[sl];
                 if (inten) inten[slice * plane + r] = I[sl];
-                if (qmu) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) qmu[(slice * K + k) * plane + r] = q * (-0.6931471805599453f * mu[sl][k]);
+                for (int k = 0; k < K; ++k) {
+                    packed[sl * K + k] = q * (-0.6931471805599453f * mu[sl][k]);
+                    if (qmu) qmu[(slice * K + k) * plane + r] = packed[sl * K + k];
                 }
                 q2 = q * q;
             }
@@ -150,6 +174,8 @@ struct FpEpiWhite {
                 if ((tid & 31) == 0) red[sl][tid >> 5] = q2;
             }
         }
+        if (sp && valid && npass == 1)   // (packed output is never combined with mirror pairing)
+            reinterpret_cast<typename VecOf<V>::T *>(sp)[((size_t)g * p.A + a) * pitch + padl + d] = pack<V>(packed);
         if (partial) {
             __syncthreads();
             if (tid < SPG && (g * SPG + tid) * K < p.nimg) {
@@ -347,6 +373,91 @@ __device__ __forceinline__ float upd_pixel(const wt_update_params &prm, const Up
         if (f.use_reg) pen += prm.beta_reg * (prm.reg_w * fabsf(xn[0] * xn[1]));
     }
     return pen;
+}
+
+// ---- K3 fused into K2: the backprojector's epilogue takes the gradient step itself -------------------------------
+// A group of V interleaved images holds V/K slices x K elements, so a pixel's thread has the whole gradient of its
+// slices in registers: x' = upd_pixel(x, gscale * W^T(q mu)) is written back (plain layout) and straight into K1's
+// packed copies VN / VT for the next forward projection -- no gradient array, no K3 pass, no re-pack (a white-beam
+// barrier iteration is K2 -> K1 -> one reduction: three launches where the separate entry points take seven).
+template <int K>
+struct BpEpiBarrierUpdate {
+    static constexpr bool kHasSums = true;
+    static constexpr int kMult = K;
+    float *x;                      // (S, K, R, C), updated in place
+    wt_update_params prm;
+    const unsigned char *active;   // (S) or null
+    double *partial;               // (S, nslots) penalty partial sums, or null
+    float *vn, *vt;                // K1's packed copies, refreshed in place
+    float gscale;                  // gradient = gscale * W^T(.)   (-1 for the white-beam data term)
+    template <int V>
+    __device__ __forceinline__ void operator()(const BpParams &p, int g, int row, int col, const float (&val)[V],
+                                               float *sums) const {
+        static_assert(V % K == 0 && V / K <= BP_MAX_SUMS, "group must hold whole slices");
+        constexpr int SPG = V / K;
+        typedef typename VecOf<V>::T VecT;
+        const size_t img = (size_t)p.R * p.C, px = (size_t)row * p.C + col;
+        float nv[V];
+#pragma unroll
+        for (int sl = 0; sl < SPG; ++sl) {
+            const int slice = g * SPG + sl;
+            const bool real = slice * K < p.nimg;
+            UpdFlags f;
+            const bool sl_on = real && (!active || active[slice]);
+            f.act = sl_on && prm.mode != WT_UPD_CLIP_ONLY;
+            f.clip = sl_on && prm.mode != WT_UPD_STEP_ONLY;
+            f.use_reg = (K == 2) && prm.reg_w != 0.0f;
+            f.use_bar = prm.t != 0.0f;
+            f.lower_only = prm.lower_only != 0;
+            f.use_triv = prm.triv_w != 0.0f;
+            f.all_elems = (prm.elem_mask & ((1u << K) - 1u)) == ((1u << K) - 1u);
+            f.fast_log = f.use_reg && f.use_bar && !f.lower_only && !f.use_triv && f.all_elems && prm.mode == WT_UPD_STEP_CLIP;
+            f.want_pen = partial != nullptr && real;
+            f.bt = prm.beta_reg * prm.t;
+            float xv[K], gv[K], xn[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                xv[k] = real ? x[((size_t)slice * K + k) * img + px] : 0.0f;
+                gv[k] = gscale * val[sl * K + k];
+            }
+            const float pen = upd_pixel<K>(prm, f, xv, gv, xn);
+            if (f.want_pen) sums[sl] += pen;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                nv[sl * K + k] = real ? xn[k] : 0.0f;
+                if (f.act || f.clip) x[((size_t)slice * K + k) * img + px] = xn[k];
+            }
+        }
+        reinterpret_cast<VecT *>(vn)[((size_t)g * p.R + row) * fp_pitch(p.C) + VPAD + col] = pack<V>(nv);
+        reinterpret_cast<VecT *>(vt)[((size_t)g * p.C + col) * fp_pitch(p.R) + VPAD + row] = pack<V>(nv);
+    }
+    template <int V>
+    __device__ __forceinline__ void finish(const BpParams &p, int g, int slot, int nslots, const float *sums) const {
+        if (!partial) return;
+        constexpr int SPG = V / K;
+#pragma unroll
+        for (int sl = 0; sl < SPG; ++sl)
+            if ((g * SPG + sl) * K < p.nimg) partial[(size_t)(g * SPG + sl) * nslots + slot] = (double)sums[sl];
+    }
+};
+
+// loss[s] = 1/2 sum_b lpart[s][b] (float partials of K1's epilogue) and pen[s] = sum_b ppart[s][b] (float64 partials of
+// K2's update epilogue), one launch: grid (S, 2), one warp each, fixed order
+__global__ void reduce_step_kernel(const float *__restrict__ lpart, int nlb, double *loss, const double *__restrict__ ppart,
+                                   int npb, double *pen) {
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    if (blockIdx.y == 0) {
+        if (!loss) return;
+        for (int b = threadIdx.x; b < nlb; b += 32) acc += (double)lpart[(size_t)s * nlb + b];
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) loss[s] = 0.5 * acc;
+    } else {
+        if (!pen || !ppart) return;
+        for (int b = threadIdx.x; b < npb; b += 32) acc += ppart[(size_t)s * npb + b];
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) pen[s] = acc;
+    }
 }
 
 // VEC = 4: every thread owns 4 consecutive pixels (16-byte loads/stores), VEC = 1: scalar fallback for

@@ -260,6 +260,49 @@ class Projector(object):
                                          _ptr(loss), S, int(a0), int(a1), _ptr(ws), nbytes, _stream()))
         return inten, qmu, loss
 
+    def step_supported(self, spectrum, nslices):
+        """whether `white_barrier_step` (the three-launch fused iteration) is available for this problem"""
+        mir = ctypes.c_int()
+        _capi.check(self.lib.wt_bp_row_info(self.handle, int(nslices * spectrum.K), None, None, ctypes.byref(mir)))
+        return spectrum.K <= 2 and not mir.value
+
+    def new_step_state(self, spectrum, nslices):
+        """device scratch that carries the packed state of `white_barrier_step` between calls (one per working set)"""
+        nbytes = int(self.lib.wt_step_workspace_bytes(self.handle, int(nslices), int(spectrum.K)))
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    @_on_own_device
+    def white_barrier_step(self, spectrum, x, meas, state, init=False, alpha=0.0, beta_reg=1.0, t=0.0, reg_w=0.0, triv_w=0.0,
+                           lower_only=False, mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None,
+                           want_loss=True, want_penalty=False):
+        """One fused inner iteration (wt_white_barrier_step): x (S, K, rows, cols) is stepped in place along
+        -W^T(q mu) with the wt_barrier_update rule, then the white-beam forward model runs at the new x.  With
+        ``init`` only the forward model runs (start of a run, or x was written from outside).  ``state`` comes from
+        `new_step_state` and must be passed unchanged from an ``init`` call on.
+        Returns (loss (S,) float64 = f at the returned x | None, penalty (S,) float64 | None)."""
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device or x.dim() != 4:
+            raise ValueError("x must be a contiguous float32 (S, K, rows, cols) tensor on %s" % self.device)
+        if spectrum.device != self.device:
+            raise ValueError("the Spectrum lives on %s, the Projector on %s" % (spectrum.device, self.device))
+        S = x.shape[0]
+        m = None
+        if meas is not None:
+            m, _ = self._as_images(meas, self.sino_shape)
+            if m.shape[0] != S:
+                raise ValueError("meas must hold one sinogram per slice")
+        prm = _capi.UpdateParams(float(alpha), float(beta_reg), float(t), float(reg_w), float(triv_w),
+                                 int(bool(lower_only)), int(mode), int(elem_mask) & 0xFFFFFFFF)
+        act = None
+        if active is not None:
+            act = active.to(torch.uint8).contiguous()
+            assert act.numel() == S
+        loss = torch.empty((S,), dtype=torch.float64, device=self.device) if want_loss else None
+        pen = torch.empty((S,), dtype=torch.float64, device=self.device) if (want_penalty and not init) else None
+        _capi.check(self.lib.wt_white_barrier_step(self.handle, spectrum.handle, _ptr(x), _ptr(m), ctypes.byref(prm), _ptr(act),
+                                                   _ptr(loss), _ptr(pen), S, _capi.STEP_INIT if init else 0, _ptr(state),
+                                                   state.numel(), _stream()))
+        return loss, pen
+
     @_on_own_device
     def mar_fp(self, vol, b, mask, inv_ngood, bt, b_hb, want_u=True, want_proj=False, want_stats=True):
         """Fused mono-MAR residual (wt_mar_fp).  vol (n, R, C); b (n, A, D); mask (n, A, D) uint8; inv_ngood (n,).

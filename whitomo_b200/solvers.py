@@ -30,13 +30,16 @@ def _as_stack(x, K):
 
 def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1, t_step=0.5, alpha=1.0,
                         beta_reg=1.0, ir_beta=0.05, max_iter=5000, do_alpha_decay=True, min_delta_loss=1e-3,
-                        n_steps_without_progress=15, add_stat_cb=None, max_total_iters=None, compact=True, stat_cb=None):
+                        n_steps_without_progress=15, add_stat_cb=None, max_total_iters=None, compact=True, stat_cb=None,
+                        fused=True):
     """Log-barrier reconstruction of element concentrations 0 <= c <= 1 with the 0.05*|c0 c1| regulariser.
 
     Defaults are the reference's run (src/barrier_method_gogo.py:184-192).  ``meas`` (S, A, D) intensities,
     ``x0`` (S, K, N, N) feasible start.  Returns (x, info) with info = dict(iters, loss (S,), trace list,
     slice_iters = projector iterations actually spent per slice).
-    Per inner iteration and slice: one fused white-beam FP (K projections), K BP, one K3 launch.
+    Per inner iteration and slice: one fused white-beam FP (K projections) and K BP whose epilogue takes the step
+    (``fused``, three launches per iteration; with a statistics callback, K > 2 or ``fused=False``: the separate entry
+    points wt_white_fp / wt_bp / wt_barrier_update, seven launches, same arithmetic).
     The loss of barrier_method's early-stop test at the new point is f(x') + penalty(x'); f(x') is the by-product
     of the FP that the next iteration's gradient needs anyway, so no projection is spent on statistics.
     ``add_stat_cb`` (alias ``stat_cb``) receives what the reference's callback receives (src/barrier_method.py:182-199):
@@ -67,23 +70,42 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
     trace = []
     slice_iters = torch.zeros(S, dtype=torch.int64, device=dev)
     min_work = -(-3 // K)                            # slices that keep the working set at >= 3 images
-    _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
+    want_pen = n_steps_without_progress is not None
+    # Fused iteration (K2 with the update in its epilogue -> K1 -> one reduction: three launches, no gradient / q*mu
+    # arrays) whenever nobody asks for the gradient (statistics callback) and the kernels offer it; else the separate
+    # entry points (seven launches).  Same arithmetic either way.
+    fused = fused and add_stat_cb is None and hasattr(proj, "step_supported") and proj.step_supported(spectrum, min(S, min_work))
+    qmu = None
+    if fused:
+        state = proj.new_step_state(spectrum, S)
+        f_loss, _ = proj.white_barrier_step(spectrum, x, meas, state, init=True)
+        state_ok = True                              # `state` holds the packed copies of the full stack x
+    else:
+        _, qmu, f_loss = proj.white_fp(spectrum, x, meas=meas, want_intensity=False)
     done = False
     for i_biter in range(n_biter):
         # working set of this barrier level: all slices; shrinks as slices stop early
         idx = torch.arange(S, device=dev)
         xw, mw, qw, fw = x, meas, qmu, f_loss
+        if fused:
+            st_w = state
+            if not state_ok:                         # the last level parked compacted results into x: re-pack
+                f_loss, _ = proj.white_barrier_step(spectrum, x, meas, state, init=True)
+                fw, state_ok = f_loss, True
         prev = None
         stall = torch.zeros(S, dtype=torch.int32, device=dev)
         active = torch.ones(S, dtype=torch.bool, device=dev)
         for i_iter in range(n_iter):
             n_w = xw.shape[0]
-            g = proj.bp(qw.reshape((n_w * K,) + proj.sino_shape), scale=-1.0)
-            if add_stat_cb is not None and (i_biter % 10 == 0 or i_biter < 30):
-                add_stat_cb(_white_barrier_stats(xw, idx, fw, g.reshape(xw.shape), beta_reg, ir_beta, t))
-            pen = proj.barrier_update(xw, g, alpha, beta_reg, t, reg_w=ir_beta, active=active,
-                                      want_penalty=n_steps_without_progress is not None)
-            _, qw, fw = proj.white_fp(spectrum, xw, meas=mw, want_intensity=False)
+            if fused:
+                fw, pen = proj.white_barrier_step(spectrum, xw, mw, st_w, alpha=alpha, beta_reg=beta_reg, t=t, reg_w=ir_beta,
+                                                  active=active, want_penalty=want_pen)
+            else:
+                g = proj.bp(qw.reshape((n_w * K,) + proj.sino_shape), scale=-1.0)
+                if add_stat_cb is not None and (i_biter % 10 == 0 or i_biter < 30):
+                    add_stat_cb(_white_barrier_stats(xw, idx, fw, g.reshape(xw.shape), beta_reg, ir_beta, t))
+                pen = proj.barrier_update(xw, g, alpha, beta_reg, t, reg_w=ir_beta, active=active, want_penalty=want_pen)
+                _, qw, fw = proj.white_fp(spectrum, xw, meas=mw, want_intensity=False)
             slice_iters[idx] += active.to(torch.int64)
             total += 1
             if n_steps_without_progress is not None:
@@ -99,18 +121,28 @@ def white_barrier_stack(proj, spectrum, meas, x0, n_iter=50, n_biter=20, t0=0.1,
                     break
                 if compact and n_active < n_w and n_active >= min_work:
                     if xw is not x:
-                        x[idx], qmu[idx], f_loss[idx] = xw, qw, fw            # park what leaves the working set
+                        x[idx], f_loss[idx] = xw, fw                      # park what leaves the working set
+                        if not fused:
+                            qmu[idx] = qw
                     else:
                         qmu, f_loss = qw, fw
                     keep = active.nonzero(as_tuple=True)[0]
                     idx = idx[keep]
-                    xw, mw, qw, fw = x[idx].contiguous(), meas[idx].contiguous(), qw[keep].contiguous(), fw[keep]
+                    xw, mw, fw = x[idx].contiguous(), meas[idx].contiguous(), fw[keep]
                     prev, stall, active = prev[keep], stall[keep], active[keep]
+                    if fused:                        # a new working set: its own packed state, forward model redone
+                        st_w = proj.new_step_state(spectrum, xw.shape[0])
+                        fw, _ = proj.white_barrier_step(spectrum, xw, mw, st_w, init=True)
+                        state_ok = False
+                    else:
+                        qw = qw[keep].contiguous()
             if max_total_iters is not None and total >= max_total_iters:
                 done = True
                 break
         if xw is not x:
-            x[idx], qmu[idx], f_loss[idx] = xw, qw, fw
+            x[idx], f_loss[idx] = xw, fw
+            if not fused:
+                qmu[idx] = qw
         else:
             qmu, f_loss = qw, fw
         t *= t_step
@@ -149,7 +181,7 @@ def _white_barrier_stats(xw, idx, f_loss, g, beta_reg, ir_beta, t):
 
 
 def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=1e-2, clip_concentrations=True,
-                    dissimilarity_constraint=True, triv_conc_constraint=True, alternate=True, start_iter=0):
+                    dissimilarity_constraint=True, triv_conc_constraint=True, alternate=True, start_iter=0, fused=True):
     """Plain gradient descent of src/white_rec.py:199-244,338-368 (flags as at :342-345, alpha/beta at :42-43):
     step = alpha*(grad + beta*(d|c0 c1| + c(c(4c-3)+1))); iteration i updates element 0 when i % 4 == 0 else
     element 1... (the reference zeroes step[1] when i % 4 == 0 and step[0] otherwise, :229-233); clip to [0, 1].
@@ -161,9 +193,16 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
     meas = meas.reshape((S,) + proj.sino_shape).to(torch.float32).contiguous()
     losses = []
     mode = _capi.UPD_STEP_CLIP if clip_concentrations else _capi.UPD_STEP_ONLY
+    reg_w = 1.0 if (dissimilarity_constraint and K == 2) else 0.0
+    triv_w = 1.0 if triv_conc_constraint else 0.0
+    fused = fused and hasattr(proj, "step_supported") and proj.step_supported(spectrum, S)
+    if fused:       # three launches per iteration (K2 + step, K1, reduction), see white_barrier_stack
+        state = proj.new_step_state(spectrum, S)
+        f_loss, _ = proj.white_barrier_step(spectrum, c, meas, state, init=True)
     for it in range(start_iter, start_iter + n_iters):
-        _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
-        g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
+        if not fused:
+            _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
+            g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
         reg_loss = 0.0
         if dissimilarity_constraint and K == 2:
             reg_loss = torch.linalg.vector_norm((beta_reg * c[:, 0] * c[:, 1]).reshape(S, -1), dim=1).double()
@@ -171,8 +210,11 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
         mask = 0xFFFFFFFF
         if alternate and K == 2:
             mask = 0b01 if it % 4 == 0 else 0b10
-        proj.barrier_update(c, g, alpha, beta_reg, 0.0, reg_w=1.0 if (dissimilarity_constraint and K == 2) else 0.0,
-                            triv_w=1.0 if triv_conc_constraint else 0.0, mode=mode, elem_mask=mask)
+        if fused:
+            f_loss, _ = proj.white_barrier_step(spectrum, c, meas, state, alpha=alpha, beta_reg=beta_reg, t=0.0, reg_w=reg_w,
+                                                triv_w=triv_w, mode=mode, elem_mask=mask)
+        else:
+            proj.barrier_update(c, g, alpha, beta_reg, 0.0, reg_w=reg_w, triv_w=triv_w, mode=mode, elem_mask=mask)
     return c, losses
 
 
@@ -298,7 +340,8 @@ def _checkpoint_key(proj, spectrum, meas_host, x0_host, params):
     return h.hexdigest()[:16]
 
 
-def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=0, world=1, checkpoint=None, **params):
+def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=0, world=1, checkpoint=None, stats=None,
+                              **params):
     """The C4 job: a stack of independent slices (host memory) reconstructed in resident batches on this rank's GPU.
 
     meas_host (S, A, D) and x0_host (S, K, N, N) are CPU tensors (pinned memory makes the copies asynchronous).  The
@@ -310,6 +353,9 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
     geometry, angles, spectrum size, solver parameters -- and the slice range, with a checksum of the batch's
     measurements); a restarted call loads the batches it finds instead of recomputing them, so a stack job that
     dies after hours resumes at the batch it was working on.  Slices are independent, so this is the whole state.
+    ``stats``: a dict that receives ``slice_iters`` (int64 tensor, one entry per slice of the rank's range: the projector
+    iterations actually spent on it -- early-stopped slices spend fewer than the schedule's maximum; -1 for slices
+    restored from a checkpoint) and ``batches``.
     Returns (x_host for the rank's range, (start, stop))."""
     from .distributed import shard_range
     s0, s1 = shard_range(meas_host.shape[0], rank, world)
@@ -374,6 +420,8 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
             np.save(f, res_host.numpy())
         os.replace(tmp, ckpt_path(b0))                    # atomic: a batch file is complete or absent
 
+    spent = torch.full((s1 - s0,), -1, dtype=torch.int64)
+    spent_dev = []
     todo = []
     for b0 in cuts[:-1]:
         done = restore(b0)
@@ -389,8 +437,10 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
         main.wait_event(ev)
         m.record_stream(main)
         x.record_stream(main)
-        res, _ = white_barrier_stack(proj, spectrum, m, x, **params)
+        res, info = white_barrier_stack(proj, spectrum, m, x, **params)
         out[b0 - s0:b1 - s0].copy_(res, non_blocking=True)
+        if info is not None:
+            spent_dev.append((b0, b1, info["slice_iters"]))
         if checkpoint:
             if pending is not None:                       # the previous batch's download has long finished
                 pending[1].synchronize()
@@ -401,6 +451,11 @@ def white_barrier_reconstruct(proj, spectrum, meas_host, x0_host, batch=8, rank=
     torch.cuda.synchronize(dev)
     if checkpoint and pending is not None:
         store(pending[0], out[pending[0] - s0:nxt_of[pending[0]] - s0])
+    if stats is not None:
+        for b0, b1, it in spent_dev:
+            spent[b0 - s0:b1 - s0] = it.cpu()
+        stats["slice_iters"] = spent
+        stats["batches"] = len(cuts) - 1
     return out, (s0, s1)
 
 
