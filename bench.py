@@ -294,23 +294,16 @@ def run_gpu(args):
     alpha, beta, t_bar, ir_beta = 1.0, 1.0, 0.1, 0.05    # src/barrier_method_gogo.py:184-192
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    marks = []
+
+    # One step = one inner barrier iteration through the fused entry point (wt_white_barrier_step): K2 over the packed
+    # q*mu of the previous forward model with the update in its epilogue -> K1 with the white-beam epilogue at the new x
+    # -> one reduction of the loss / penalty partial sums.  K FP + K BP per slice, three launches.
+    state = proj.new_step_state(spec, S)
+    proj.white_barrier_step(spec, x, meas, state, init=True)
 
     def step(timed):
-        m = [ev() for _ in range(4)] if timed else None
-        if timed:
-            m[0].record()
-        _, qmu, loss = proj.white_fp(spec, x, meas=meas, want_intensity=False)
-        if timed:
-            m[1].record()
-        g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
-        if timed:
-            m[2].record()
-        pen = proj.barrier_update(x, g, alpha, beta, t_bar, reg_w=ir_beta, want_penalty=True)
-        if timed:
-            m[3].record()
-            marks.append(m)
-        return loss, pen
+        return proj.white_barrier_step(spec, x, meas, state, alpha=alpha, beta_reg=beta, t=t_bar, reg_w=ir_beta,
+                                       want_penalty=True, timed=timed)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -330,6 +323,7 @@ def run_gpu(args):
     sync_all()
     elapsed = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if sampler else None
+    bp_ms, fp_ms = proj.step_times(min(args.steps, 64))        # device events recorded inside the timed steps
     if world > 1:
         tt = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -337,6 +331,43 @@ def run_gpu(args):
     final_loss = float(loss.sum().item())
     if not np.isfinite(final_loss):
         raise SystemExit("bench.py: non-finite data-fidelity loss after the timed region")
+
+    # what the reference-faithful positions cost: the same step with closed-form positions (not part of `value`)
+    pos_cost = None
+    if rank == 0 and proj.positions == "astra":
+        proj_x = Projector(N, N, D, np.linspace(0, np.pi, A), device=dev, positions="exact")
+        x2 = x0.clone()
+        st2 = proj_x.new_step_state(spec, S)
+        proj_x.white_barrier_step(spec, x2, meas, st2, init=True)
+        for _ in range(2):
+            proj_x.white_barrier_step(spec, x2, meas, st2, alpha=alpha, beta_reg=beta, t=t_bar, reg_w=ir_beta, want_penalty=True)
+        g0, g1 = ev(), ev()
+        g0.record()
+        for _ in range(3):
+            proj_x.white_barrier_step(spec, x2, meas, st2, alpha=alpha, beta_reg=beta, t=t_bar, reg_w=ir_beta, want_penalty=True, timed=True)
+        g1.record()
+        torch.cuda.synchronize()
+        bx, fx = proj_x.step_times(3)
+        pos_cost = {"ms_per_step_exact_positions": g0.elapsed_time(g1) / 3, "ms_per_step_timed": elapsed / args.steps * 1e3,
+                    "kernel_ms_exact": {"white_fp": float(np.mean(fx)), "bp_update": float(np.mean(bx))},
+                    "note": "positions='exact' evaluates c0 + l*delta in closed form: 1.1e-4 (FP) / 2.5e-4..7.2e-4 (BP) away from "
+                            "the reference at this size (profiles/r2_parity_fullsize.json); the timed mode repeats the "
+                            "reference's float32 running sum (9e-7 / 3e-6)"}
+        del proj_x, x2, st2
+    # K3 on its own (wt_barrier_update, the HBM-bound streaming kernel the separate entry points use; inside the timed
+    # step its work rides in K2's epilogue)
+    gsep = torch.empty_like(x0)
+    xs = x0.clone()
+    for _ in range(2):
+        proj.barrier_update(xs, gsep.zero_(), alpha, beta, t_bar, reg_w=ir_beta, want_penalty=True)
+    u0, u1 = ev(), ev()
+    u0.record()
+    for _ in range(5):
+        proj.barrier_update(xs, gsep, 0.0, beta, t_bar, reg_w=ir_beta, want_penalty=True)
+    u1.record()
+    torch.cuda.synchronize()
+    t_up = u0.elapsed_time(u1) / 5 * 1e-3
+    del gsep, xs
 
     # ---- end-to-end arm: host buffers in, host buffers out, through the same public calls ------------
     h_x = torch.empty((S, K, N, N), dtype=torch.float32).pin_memory()
@@ -416,16 +447,17 @@ def run_gpu(args):
 
     upd_per_step = 2.0 * K * N * N * A * S * world          # K FP + K BP per slice, all ranks
     value = upd_per_step * args.steps / elapsed / 1e9
-    t_fp = float(np.mean([m[0].elapsed_time(m[1]) for m in marks])) * 1e-3
-    t_bp = float(np.mean([m[1].elapsed_time(m[2]) for m in marks])) * 1e-3
-    t_up = float(np.mean([m[2].elapsed_time(m[3]) for m in marks])) * 1e-3
+    t_fp = float(np.mean(fp_ms)) * 1e-3
+    t_bp = float(np.mean(bp_ms)) * 1e-3
     hbm, which = peaks()
     ceil_gups, ceil_src = onchip_ceiling()
     th = np.linspace(0, np.pi, A)
     fp_work = float(np.mean(np.maximum(np.abs(np.cos(th)), np.abs(np.sin(th)))))     # 0.9003
-    # algorithmic bytes per launch: fused white FP reads K*N^2 + A*D (meas), writes K*A*D (q*mu)
+    # algorithmic bytes per launch: fused white FP reads K*N^2 + A*D (meas), writes K*A*D (q*mu);
+    # K2 with the update epilogue reads K*A*D (q*mu) + K*N^2 (x), writes K*N^2 (x') -- the packed copies it also
+    # refreshes are implementation traffic, not algorithmic
     fp_bytes = 4.0 * (K * N * N + A * D + K * A * D) * S
-    bp_bytes = 4.0 * (K * A * D + K * N * N) * S
+    bp_bytes = 4.0 * (K * A * D + 2 * K * N * N) * S
     up_bytes = 12.0 * K * N * N * S
     roof = lambda b, tm, kern: {"bound": "hbm", "achieved": b / tm / 1e9, "peak": hbm, "unit": "GB/s",
                                 "frac": b / tm / 1e9 / hbm, "traffic": ncu_traffic(kern, S), "algorithmic_bytes": b,
@@ -441,7 +473,7 @@ def run_gpu(args):
                    "cpu_affinity": "NVML ideal CPU set of the rank's GPU" if numa_bound else "default"},
         "barrier_iters_per_s": S * world * args.steps / elapsed,
         "fp_gups": K * N * N * A * S / t_fp / 1e9, "bp_gups": K * N * N * A * S / t_bp / 1e9,
-        "kernel_ms": {"white_fp": t_fp * 1e3, "bp": t_bp * 1e3, "barrier_update": t_up * 1e3},
+        "kernel_ms": {"white_fp": t_fp * 1e3, "bp_with_update_epilogue": t_bp * 1e3, "barrier_update_standalone": t_up * 1e3},
         # shared-memory bytes per update: K1 reads 2 taps x 16 B per 4 updates, but only N^2*A*mean(max(|cos|,|sin|)) tap
         # pairs per image (rays are 1/max(|cos|,|sin|) positions apart on a line); K2 reads 3 taps x 16 B per 8 updates
         # (a vertically adjacent pixel pair shares its taps), i.e. 6 B per update where separate taps would need 8
@@ -452,7 +484,8 @@ def run_gpu(args):
                    "fp_frac": K * N * N * A * S / t_fp / 1e9 / (ceil_gups / fp_work),
                    "bp_frac": K * N * N * A * S / t_bp / 1e9 / (ceil_gups * 8.0 / 6.0)},
         "roofline": None, "roofline_other": None,
-        "roofline_update": dict(roof(up_bytes, t_up, "update"), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3)"),
+        "roofline_update": dict(roof(up_bytes, t_up, "update"), kernel="barrier_update_kernel<2> + penalty reduce (HBM-bound K3), timed on "
+                                "its own after the timed region: inside the step its work is K2's epilogue"),
         "e2e": {"value": upd_per_step * args.steps / e2e_elapsed / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": int(S * K * N * N * 4 + S * A * D * 4) * world,
                 "d2h_bytes_per_step": int(S * K * N * N * 4 + S * 8) * world,
@@ -461,14 +494,15 @@ def run_gpu(args):
                         "through Projector.white_fp/bp/barrier_update, updated concentrations + loss -> pinned host; "
                         "the slices of a step travel in sub-batches of 2 whose copies overlap the kernels of the "
                         "neighbouring sub-batch on separate streams"},
-        "gpu_launches": 7 * args.steps,   # per step: pack_vol, fp, reduce, pack_sino, bp, barrier_update, reduce
+        "gpu_launches": 3 * args.steps,   # per step: bp_kernel (update epilogue), fp_kernel (white epilogue), reduce_step_kernel
         "clocks": clocks,
         "loss_after": final_loss,
         "positions": proj.positions,
+        "positions_cost": pos_cost,
     }
     if c5 is not None:
         out["c5_angle_split"] = c5
-    tot = t_fp + t_bp + t_up
+    tot = t_fp + t_bp
     note = ("gather/stencil kernel with ~N-fold on-chip reuse: bound by shared-memory load bandwidth (see `onchip`), "
             "not HBM (SURVEY 8d: compulsory-bytes ceiling of the HBM fraction is ~0.4%)")
     r_fp = dict(roof(fp_bytes, t_fp, "fp"), kernel="fp_kernel<4, white epilogue> (TMA-staged ray-driven Joseph FP), "
@@ -477,7 +511,7 @@ def run_gpu(args):
                 "the volume (row-major for vertical angles, transposed for horizontal ones) where the algorithmic "
                 "count has one; the detector-block-major launch order keeps the lines in flight L2-resident, so each "
                 "copy comes from DRAM once (tile-major order read 9.2 GB, with alternating sweeps 4.1 GB)")
-    r_bp = dict(roof(bp_bytes, t_bp, "bp"), kernel="bp_kernel<4> (TMA-staged pixel-driven gather), %.0f%% of the step"
+    r_bp = dict(roof(bp_bytes, t_bp, "bp"), kernel="bp_kernel<4, barrier-update epilogue> (TMA-staged pixel-driven gather), %.0f%% of the step"
                 % (100 * t_bp / tot), note=note)
     out["roofline"], out["roofline_other"] = (r_fp, r_bp) if t_fp >= t_bp else (r_bp, r_fp)    # dominant kernel first
     if world == 1 and not args.no_cpu:

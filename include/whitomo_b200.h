@@ -184,10 +184,17 @@ typedef struct {
  * untouched, from a WT_STEP_INIT call on; any other use of it, a change of nslices, or writing x from outside
  * requires a new WT_STEP_INIT. */
 #define WT_STEP_INIT 1
+#define WT_STEP_TIMED 2   /* diagnostic: record CUDA events around K2 and K1 of this step (see wt_step_times) */
+#define WT_STEP_RING 64
 size_t wt_step_workspace_bytes(const wt_geom *g, int nslices, int n_elements);
 int wt_white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, const float *meas,
                           const wt_update_params *prm, const unsigned char *active, double *loss, double *penalty,
                           int nslices, int flags, void *ws, size_t ws_bytes, void *stream);
+
+/* Diagnostic (no counterpart in the reference): device durations of K2 (with the update epilogue) and K1 (white-beam
+ * epilogue) of the most recent WT_STEP_TIMED steps on this geometry, oldest first, at most max_steps (<= WT_STEP_RING);
+ * waits for those steps to finish.  Returns the number of steps written, or a negative error. */
+int wt_step_times(const wt_geom *g, int max_steps, float *bp_ms, float *fp_ms);
 
 int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, size_t npix,
                       const wt_update_params *prm, const unsigned char *active, double *penalty, void *ws,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "wt_step_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "wt_white_barrier_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_void_p, c_size_t, c_void_p]),
+    "wt_step_times": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
     "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
 }
@@ -52,7 +53,7 @@ class UpdateParams(ctypes.Structure):
 
 UPD_STEP_CLIP, UPD_STEP_ONLY, UPD_CLIP_ONLY = 0, 1, 2
 POS_ASTRA, POS_EXACT = 0, 1
-STEP_INIT = 1
+STEP_INIT, STEP_TIMED, STEP_RING = 1, 2, 64
 
 _lib = None
 

@@ -421,6 +421,7 @@ int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float
     wt_geom *g = new wt_geom();
     g->rows = rows; g->cols = cols; g->ndet = ndet; g->nangles = nangles; g->det_width = det_width;
     g->positions = positions;
+    g->step_ev = nullptr; g->step_count = 0;
     // zero margins of the packed sinogram: every staged segment of every tile must stay inside a row (the reference's
     // running sums displace a pixel's detector coordinate by up to N * ulp(2N) / 2: 0.25 at 2048^2, 4 at 8192^2)
     const double halfdiag = 0.5 * sqrt((double)rows * rows + (double)cols * cols) / (double)det_width;
@@ -473,6 +474,10 @@ void wt_geom_destroy(wt_geom *g) {
     if (g->d_bwarpd) cudaFree(g->d_bwarpd);
     if (g->d_tiles) cudaFree(g->d_tiles);
     if (g->d_order) cudaFree(g->d_order);
+    if (g->step_ev) {
+        for (int i = 0; i < 3 * WT_STEP_RING; ++i) cudaEventDestroy(g->step_ev[i]);
+        free(g->step_ev);
+    }
     free(g->h_angles);
     free(g->h_vertical);
     delete g;
@@ -762,6 +767,17 @@ static int white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, 
     double *ppart = cv.take<double>((size_t)nslices * nslots);
     if (!cv.ok()) { g_err = "wt_white_barrier_step: workspace too small (wt_step_workspace_bytes)"; return WT_ERR_WORKSPACE; }
     const Chunk c = chunk_of(n);
+    cudaEvent_t *ev = nullptr;
+    if ((flags & WT_STEP_TIMED) && !(flags & WT_STEP_INIT)) {
+        wt_geom *gm = const_cast<wt_geom *>(g);
+        if (!gm->step_ev) {
+            gm->step_ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * 3 * WT_STEP_RING);
+            for (int i = 0; i < 3 * WT_STEP_RING; ++i) WT_CUDA(cudaEventCreate(&gm->step_ev[i]));
+        }
+        ev = gm->step_ev + 3 * (gm->step_count % WT_STEP_RING);
+        gm->step_count++;
+        WT_CUDA(cudaEventRecord(ev[0], st));
+    }
     if (flags & WT_STEP_INIT) {
         // packed copies of x (with their zero padding) and an all-zero packed sinogram buffer (K1 only writes detectors
         // [0, ndet) of every row); no update: the forward model below then produces q*mu and f(x) of the start point
@@ -777,12 +793,14 @@ static int white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, 
         be.x = x; be.prm = *prm; be.active = active; be.partial = penalty ? ppart : nullptr; be.vn = vn; be.vt = vt; be.gscale = -1.0f;
         const int rc = run_bp(g, nullptr, n, 0, g->nangles, sp, be, st, 0, -1, true);
         if (rc) return rc;
+        if (ev) WT_CUDA(cudaEventRecord(ev[1], st));
     }
     HFpWhite<K> e;
     e.tab = s->d_tab; e.E = s->E; e.cslot = s->cslot; e.meas = meas; e.inten = nullptr; e.qmu = nullptr;
     e.partial = loss ? lpart : nullptr; e.sp = sp; e.padl = g->sino_padl; e.pitch = g->sino_pitch;
     const int nb = run_fp(g, x, n, 0, g->nangles, vn, vt, e, st, true);
     if (nb < 0) return nb;
+    if (ev) WT_CUDA(cudaEventRecord(ev[2], st));
     if (loss || (penalty && !(flags & WT_STEP_INIT))) {
         reduce_step_kernel<<<dim3(nslices, 2), 32, 0, st>>>(lpart, nb, loss, (flags & WT_STEP_INIT) ? nullptr : ppart, nslots,
                                                              (flags & WT_STEP_INIT) ? nullptr : penalty);
@@ -792,6 +810,20 @@ static int white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, 
 }
 
 extern "C" {
+
+int wt_step_times(const wt_geom *g, int max_steps, float *bp_ms, float *fp_ms) {
+    if (!g || !bp_ms || !fp_ms || max_steps < 0) return WT_ERR_INVALID;
+    if (!g->step_ev) return 0;
+    const long long have = g->step_count < WT_STEP_RING ? g->step_count : WT_STEP_RING;
+    const int n = (int)(have < max_steps ? have : max_steps);
+    for (int i = 0; i < n; ++i) {        // the n most recent timed steps, oldest first
+        const cudaEvent_t *ev = g->step_ev + 3 * ((g->step_count - n + i) % WT_STEP_RING);
+        if (cudaEventSynchronize(ev[2]) != cudaSuccess) return WT_ERR_CUDA;
+        if (cudaEventElapsedTime(&bp_ms[i], ev[0], ev[1]) != cudaSuccess) return WT_ERR_CUDA;
+        if (cudaEventElapsedTime(&fp_ms[i], ev[1], ev[2]) != cudaSuccess) return WT_ERR_CUDA;
+    }
+    return n;
+}
 
 int wt_white_barrier_step(const wt_geom *g, const wt_spectrum *s, float *x, const float *meas, const wt_update_params *prm,
                           const unsigned char *active, double *loss, double *penalty, int nslices, int flags, void *ws,

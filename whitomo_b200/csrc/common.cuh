@@ -154,7 +154,10 @@ struct wt_geom {
     int nphase;
     int phase_start[5];
     float *h_angles;
-    unsigned char *h_vertical;   // per angle: 1 if the projector marches over rows (reads VN), 0 if over columns (VT)
+    unsigned char *h_vertical;
+    // optional device timestamps of the fused step (WT_STEP_TIMED): ring of (before K2, after K2, after K1) events
+    cudaEvent_t *step_ev;
+    long long step_count;   // per angle: 1 if the projector marches over rows (reads VN), 0 if over columns (VT)
 };
 
 struct wt_spectrum {

@@ -274,7 +274,7 @@ class Projector(object):
     @_on_own_device
     def white_barrier_step(self, spectrum, x, meas, state, init=False, alpha=0.0, beta_reg=1.0, t=0.0, reg_w=0.0, triv_w=0.0,
                            lower_only=False, mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None,
-                           want_loss=True, want_penalty=False):
+                           want_loss=True, want_penalty=False, timed=False):
         """One fused inner iteration (wt_white_barrier_step): x (S, K, rows, cols) is stepped in place along
         -W^T(q mu) with the wt_barrier_update rule, then the white-beam forward model runs at the new x.  With
         ``init`` only the forward model runs (start of a run, or x was written from outside).  ``state`` comes from
@@ -299,9 +299,19 @@ class Projector(object):
         loss = torch.empty((S,), dtype=torch.float64, device=self.device) if want_loss else None
         pen = torch.empty((S,), dtype=torch.float64, device=self.device) if (want_penalty and not init) else None
         _capi.check(self.lib.wt_white_barrier_step(self.handle, spectrum.handle, _ptr(x), _ptr(m), ctypes.byref(prm), _ptr(act),
-                                                   _ptr(loss), _ptr(pen), S, _capi.STEP_INIT if init else 0, _ptr(state),
-                                                   state.numel(), _stream()))
+                                                   _ptr(loss), _ptr(pen), S,
+                                                   (_capi.STEP_INIT if init else 0) | (_capi.STEP_TIMED if timed else 0),
+                                                   _ptr(state), state.numel(), _stream()))
         return loss, pen
+
+    def step_times(self, max_steps=_capi.STEP_RING):
+        """(bp_ms, fp_ms) lists of the most recent ``timed`` fused steps (device events recorded inside the call)"""
+        n = min(int(max_steps), _capi.STEP_RING)
+        b, f = (ctypes.c_float * n)(), (ctypes.c_float * n)()
+        got = self.lib.wt_step_times(self.handle, n, b, f)
+        if got < 0:
+            _capi.check(got)
+        return list(b[:got]), list(f[:got])
 
     @_on_own_device
     def mar_fp(self, vol, b, mask, inv_ngood, bt, b_hb, want_u=True, want_proj=False, want_stats=True):
