@@ -45,9 +45,9 @@ def onchip_ceiling():
 
 def ncu_traffic(kernel, slices):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-    command at the same slices-per-step (profiles/r1_traffic_s8_v3.json); None for any other configuration."""
+    command at the same slices-per-step (profiles/r2_traffic_s8.json); None for any other configuration."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic_s8_v3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic_s8.json")) as f:
             t = json.load(f)
         return float(t[kernel]["traffic_bytes"]) if slices == 8 else None
     except Exception:

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
             atomicMin(&sm.lo, l_lo);
             atomicMax(&sm.hi, l_hi);
         }
-        if (!valid) l_lo = l_hi = 0;
+        if (!valid || l_hi <= l_lo) l_lo = l_hi = 0;    // (a ray that misses the volume has nothing to skip to either)
     }
     __syncthreads();
     const int Lb = sm.lo, Le = sm.hi;
