@@ -1,7 +1,9 @@
 // Shared device helpers and the geometry handle of the whitomo_b200 engine (sm_100a only).
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <stdio.h>
 #include <string>
 
@@ -263,17 +265,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// A warp whose data has not arrived yields its issue slots for a moment instead of spinning: on small problems the
+// consumers otherwise starve the one warp that could feed them (the producer shares their schedulers).
+#ifndef WT_WAIT_SLEEP_NS
+#define WT_WAIT_SLEEP_NS 32
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WT_WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra WT_DONE_%=;\n"
-        "bra WT_WAIT_%=;\n"
+        "WT_WAIT_%=:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WT_WAIT_%=;\n"
         "WT_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "n"(WT_WAIT_SLEEP_NS)
         : "memory");
 }
 // global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` in bytes.
@@ -281,6 +290,19 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// global -> shared tiled copies (one box of a tensor map); coordinates innermost first
+__device__ __forceinline__ void tma_load_tile_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_tile_3d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {

@@ -46,6 +46,14 @@ constexpr int FP_STAGES = WT_FP_STAGES;
 // (the 9th position of the margin absorbs the residual of the warped closed form that places the windows)
 constexpr int FP_WFIT = FP_W - 9;
 constexpr int FP_MAX_PHASES = 4;
+// Staging copies of a chunk: ONE tiled TMA copy (cp.async.bulk.tensor, a box of FP_LB lines x FP_W positions of the
+// packed copy) instead of FP_LB one-line bulk copies.  A per-lane cp.async.bulk compiles to a vote / R2UR loop that
+// issues the lanes' copies one after the other at ~150 cycles each: 1.2 us per chunk, which is all of the kernel at
+// 256^2 (time proportional to the number of copies, whatever their size or the pipeline depth) and, with four CTAs per
+// SM, within 25 % of the chunk time at 2048^2.  WT_FP_TENSOR_TMA=0 keeps the one-line copies.
+#ifndef WT_FP_TENSOR_TMA
+#define WT_FP_TENSOR_TMA 1
+#endif
 
 __host__ __device__ inline int fp_pitch(int npos) {
     int p = npos + 2 * VPAD;
@@ -193,28 +201,28 @@ struct FpSmem {
     uint64_t empty[FP_STAGES];  // all consumer warps are done reading a stage
     float wstart[FP_STAGES];
     float zmin[FP_AT], delta[FP_AT];   // per angle of the tile: left-most ray at line 0 in unwarped coordinates, slope
-    alignas(16) WarpAngleF wtab[FP_AT];   // the angles' position warps (stored as float4)
+    // the angles' position warps, entry-major: the producer's 8 lanes (one per angle) read 8 consecutive words
+    float wg[16][FP_AT], wi[16][FP_AT];
     int lo, hi;                                    // line range any ray of the CTA needs
 };
 
-// float versions of warp_g / warp_ginv over the shared-memory copy of one angle's table
-__device__ __forceinline__ float warp_g_f(const float *gcum, const float *islope, float c) {
+// float versions of warp_g / warp_ginv over the shared-memory copy of the tile's tables (column `k` = angle slot)
+__device__ __forceinline__ float warp_g_f(const float (*wg)[FP_AT], const float (*wi)[FP_AT], int k, float c) {
     const float a = fabsf(c);
     int i = 0;
 #pragma unroll
     for (int j = 1; j < WT_NB; ++j)
         if (a >= (float)(2 << j)) i = j;
     const float pos = i ? (float)(2 << i) : 0.0f;
-    return copysignf(gcum[i] + __fdividef(a - pos, islope[i]), c);
+    return copysignf(wg[i][k] + __fdividef(a - pos, wi[i][k]), c);
 }
-__device__ __forceinline__ float warp_ginv_f(const float *gcum, const float *islope, float z) {
+// `si`: the stripe of the previous query (rays move monotonically, a stripe or less per chunk): usually two loads
+__device__ __forceinline__ float warp_ginv_f(const float (*wg)[FP_AT], const float (*wi)[FP_AT], int k, float z, int &si) {
     const float a = fabsf(z);
-    int i = 0;
-#pragma unroll
-    for (int j = 1; j < WT_NB; ++j)
-        if (a >= gcum[j]) i = j;
-    const float pos = i ? (float)(2 << i) : 0.0f;
-    return copysignf(fmaf(a - gcum[i], islope[i], pos), z);
+    while (si > 0 && a < wg[si][k]) --si;
+    while (si + 1 < WT_NB && a >= wg[si + 1][k]) ++si;
+    const float pos = si ? (float)(2 << si) : 0.0f;
+    return copysignf(fmaf(a - wg[si][k], wi[si][k], pos), z);
 }
 
 // Epilogue contract: epi.operator()<W>(p, g, a, d, valid, val[W], cta_scratch, pass, npass) handles the W images of
@@ -222,7 +230,8 @@ __device__ __forceinline__ float warp_ginv_f(const float *gcum, const float *isl
 // MIRROR the V components are V/2 images x {ray (a, d), mirrored ray (a, D-1-d)}: the epilogue then runs twice with
 // W = V/2, pass = 0, 1 of npass = 2 (per-CTA partial sums are laid out per pass).
 template <int V, class Epi, bool MIRROR>
-__global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
+__global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const __grid_constant__ CUtensorMap tm_vn,
+                                                      const __grid_constant__ CUtensorMap tm_vt) {
     typedef typename VecOf<V>::T VecT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FpSmem<V> &sm = *reinterpret_cast<FpSmem<V> *>(smem_raw);
@@ -257,8 +266,12 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         sm.lo = nlines;
         sm.hi = 0;
     }
-    if (tid < FP_AT * 8 && (tid >> 3) < tile.count)      // the angles' position warps: 8 x 16 bytes per angle
-        reinterpret_cast<float4 *>(&sm.wtab[tid >> 3])[tid & 7] = __ldg(reinterpret_cast<const float4 *>(p.warpf + tile.first + (tid >> 3)) + (tid & 7));
+    if (tid < FP_AT * 8 && (tid >> 3) < tile.count) {    // the angles' position warps: 8 x 16 bytes per angle
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p.warpf + tile.first + (tid >> 3)) + (tid & 7));
+        float (*dst)[FP_AT] = (tid & 4) ? sm.wi : sm.wg;          // WarpAngleF = gcum[16], islope[16]
+        const int e = 4 * (tid & 3), k = tid >> 3;
+        dst[e][k] = v.x; dst[e + 1][k] = v.y; dst[e + 2][k] = v.z; dst[e + 3][k] = v.w;
+    }
     __syncthreads();
     if (tid < FP_AT) {
         // the left-most of the tile's rays of this angle at line 0 (detectors d0 .. min(d0+DT, D)-1) in unwarped
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
             const int dl_ = min(d0 + FP_DT, p.Dproc) - 1;
             const double ca = an.c0_base + ((double)d0 + 0.5) * an.c0_step;
             const double cb = an.c0_base + ((double)dl_ + 0.5) * an.c0_step;
-            lo_z = warp_g_f(sm.wtab[tid].gcum, sm.wtab[tid].islope, (float)fmin(ca, cb));
+            lo_z = warp_g_f(sm.wg, sm.wi, tid, (float)fmin(ca, cb));
             dl = an.delta;
         }
         sm.zmin[tid] = lo_z;
@@ -296,8 +309,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         // lines on which floor(c) can be inside [-1, npos-1], from the warped closed form G(c_l) = G(c_0) + l delta;
         // the estimate may be off by a line on each side (and by the 5e-3 pixel residual of the warp), which the
         // zero padding absorbs (|delta| <= 1, VPAD = 4)
-        const float *gc = sm.wtab[slot].gcum, *is = sm.wtab[slot].islope;
-        const float z0 = warp_g_f(gc, is, c0), zn = warp_g_f(gc, is, (float)npos);
+        const float z0 = warp_g_f(sm.wg, sm.wi, slot, c0), zn = warp_g_f(sm.wg, sm.wi, slot, (float)npos);
         if (fabsf(delta) * (float)nlines < 0.5f) {
             const bool hit = (c0 > -2.0f) && (c0 < (float)npos + 1.0f);
             l_lo = 0;
@@ -324,6 +336,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
 
     // producer warp: where the window of chunk `ch` (the ch-th chunk of FP_LB lines, ascending: the reference's
     // summation order) starts -- computed BEFORE the producer waits for the stage to be released
+    int stripe = 0;          // producer lanes: stripe of the lane's angle at the last planned chunk
     auto plan = [&](int ch) {
         const int l0 = Lb + ch * FP_LB;
         const int l1 = min(l0 + FP_LB, nlines) - 1;
@@ -333,7 +346,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
             const float zm = sm.zmin[lane], dl = sm.delta[lane];
             if (zm < 1.0e38f) {
                 const float za = fmaf((float)l0, dl, zm), zb = fmaf((float)l1, dl, zm);
-                if (p.astra) m = fminf(warp_ginv_f(sm.wtab[lane].gcum, sm.wtab[lane].islope, za), warp_ginv_f(sm.wtab[lane].gcum, sm.wtab[lane].islope, zb));
+                if (p.astra) m = fminf(warp_ginv_f(sm.wg, sm.wi, lane, za, stripe), warp_ginv_f(sm.wg, sm.wi, lane, zb, stripe));
                 else m = fminf(za, zb);          // the warp is the identity
             }
         }
@@ -352,12 +365,23 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
         if (lane == 0) {
             fence_proxy_async();                     // consumers' generic-proxy reads of this stage precede the refill
             sm.wstart[s] = (float)(ws - VPAD);       // position of window slot 0
-            mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nl * FP_W * sizeof(VecT)));
+            // (a tiled copy always delivers the whole box: lines past the volume's end arrive as zeros or as the next
+            // group's lines and are never read)
+            mbar_arrive_expect_tx(&sm.full[s], (uint32_t)((WT_FP_TENSOR_TMA ? FP_LB : nl) * FP_W * sizeof(VecT)));
         }
         __syncwarp();
-        if (lane < nl)
-            tma_load_1d(&sm.seg[s][lane][0], base + (size_t)(l0 + lane) * pitch + ws, (uint32_t)(FP_W * sizeof(VecT)),
-                        &sm.full[s]);
+        if constexpr (WT_FP_TENSOR_TMA) {
+            if (lane == 0) {
+                const CUtensorMap *tm = an0.vertical ? &tm_vn : &tm_vt;
+                const int line = g * nlines + l0;
+                // coordinates in elements of the map: floats for V = 1, 2; 8-byte words for V = 4 (fp_tensor_map)
+                tma_load_tile_2d(&sm.seg[s][0][0], tm, V == 4 ? ws * 2 : ws * V, line, &sm.full[s]);
+            }
+        } else {
+            if (lane < nl)
+                tma_load_1d(&sm.seg[s][lane][0], base + (size_t)(l0 + lane) * pitch + ws, (uint32_t)(FP_W * sizeof(VecT)),
+                            &sm.full[s]);
+        }
     };
 
     float acc[V];
@@ -458,6 +482,33 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi) {
     }
 }
 
+// Tensor map of one packed copy (G groups x nlines lines x pitch positions x V floats) as a rank-2 tensor (position, line)
+// with a box of FP_LB lines x FP_W positions.  TMA boxes end at 256 elements per dimension: V = 1, 2 count in floats
+// (96 / 192 per line), V = 4 in 8-byte words (192 per line; a rank-3 map with the four components as its innermost
+// 16-byte dimension works too but moves the box 16 bytes at a time: 1.5x slower than the one-line copies).
+inline cudaError_t fp_tensor_map(CUtensorMap *tm, const float *packed, int V, int pitch, size_t total_lines) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = (EncodeFn)fn;
+    }
+    const int per_pos = V == 4 ? 2 : V;          // map elements per position
+    cuuint64_t dims[2] = {(cuuint64_t)pitch * per_pos, (cuuint64_t)total_lines};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * V * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)(FP_W * per_pos), (cuuint32_t)FP_LB}, estr[2] = {1, 1};
+    const CUresult r = encode(tm, V == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)packed, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int V, class Epi, bool MIRROR = false>
 inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
     const size_t smem = sizeof(FpSmem<V>);
@@ -471,8 +522,17 @@ inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cuda
     }
     FpParams q = p;
     q.ndblk = (p.Dproc + FP_DT - 1) / FP_DT;
+    // tensor maps of the two packed copies (host-side encoding of a few hundred bytes; they travel as kernel parameters)
+    alignas(64) CUtensorMap tm_vn, tm_vt;
+    memset(&tm_vn, 0, sizeof(tm_vn));
+    memset(&tm_vt, 0, sizeof(tm_vt));
+    if (WT_FP_TENSOR_TMA) {
+        cudaError_t e = fp_tensor_map(&tm_vn, p.vn, V, fp_pitch(p.C), (size_t)groups * p.R);
+        if (e == cudaSuccess) e = fp_tensor_map(&tm_vt, p.vt, V, fp_pitch(p.R), (size_t)groups * p.C);
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid(q.ndblk * p.ntiles, 1, groups);
-    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(q, epi);
+    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(q, epi, tm_vn, tm_vt);
     return cudaSuccess;
 }
 
