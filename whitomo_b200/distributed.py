@@ -33,13 +33,15 @@ def angle_ranges(n_angles, world, align=8):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
-def angle_ranges_by_cost(tile_first, tile_count, n_angles, world, fp_share=0.55, tile_angles=8):
+def angle_ranges_by_cost(tile_first, tile_count, n_angles, world, fp_share=0.55, tile_overhead=0.12, tile_angles=8):
     """Angle ranges per rank that balance the projector COST instead of the angle count.  The forward projector runs
-    one CTA column per angle tile whatever the tile holds (tiles around 45/135 degrees hold fewer than 8 angles: their
-    rays diverge faster than one staging window allows), the backprojector's cost is per angle.  With equal angle
-    counts the ranks around 45/135 degrees ran 8 % longer (profiles/r1_c5_anglesplit.json).  Cuts fall on tile
-    boundaries.  tile_first / tile_count: the plan of wt_geom_plan."""
-    cost = [fp_share * tile_angles + (1.0 - fp_share) * c for c in tile_count]
+    one CTA column per angle tile; a tile that holds fewer than 8 angles (tiles around 45/135 degrees: their rays
+    diverge faster than one staging window allows) gathers proportionally less but keeps its per-tile overhead
+    (staging, idle ray slots): measured, an angle of such a tile costs K1 about 8 % more (profiles/r1_c5_anglesplit.json;
+    weighting tiles as if their cost did not depend on their angle count made the split WORSE: profiles/r2_bench_8gpu.json
+    first run).  The backprojector's cost is per angle.  Cuts fall on tile boundaries.  tile_first / tile_count: the plan
+    of wt_geom_plan."""
+    cost = [fp_share * (tile_overhead * tile_angles + (1.0 - tile_overhead) * c) + (1.0 - fp_share) * c for c in tile_count]
     total = float(sum(cost))
     cuts, acc, r = [0], 0.0, 1
     for f, c, w in zip(tile_first, tile_count, cost):
