@@ -51,6 +51,13 @@ int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *ang
                  int *tile_first, int *tile_count, int *tile_vertical, int *launch_order, int *n_tiles, int *n_phases,
                  int *phase_start);
 
+/* Diagnostic, host only: how small problems are spread over the SMs.  A geometry with fewer (angle tile, detector
+ * block) pairs than the SMs hold CTAs has each pair's lines split over a thread-block cluster of *fp_split CTAs (K1); a
+ * volume with fewer pixel tiles than SMs has each tile's angles split over *bp_split CTAs (K2); rank 0 of the cluster adds
+ * the partial sums in rank order over distributed shared memory, so results stay deterministic.  1 = no split.  Both
+ * depend on the geometry alone.  n_tiles: the tile count wt_geom_plan reports. */
+int wt_split_plan(int rows, int cols, int ndet, int nangles, int n_tiles, int *fp_split, int *bp_split, int *bp_tile_rows);
+
 /* Replaces astra.create_proj_geom('parallel', det_width, ndet, angles) + astra.create_vol_geom(rows, cols)
  * + astra.create_projector('linear', pg, vg)  (src/white_projection.py:41-63, src/white_rec.py:66-74,
  * teeth_recon/experiments.py:228-235).  `angles` is a HOST array (radians, cast to float32 like ASTRA). */

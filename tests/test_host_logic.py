@@ -254,3 +254,18 @@ def test_launch_order_visits_every_cta_once(n, na, ndblk):
     # consecutive CTAs share the detector block except at block / phase boundaries
     changes = sum(1 for (t0, b0), (t1, b1) in zip(seen, seen[1:]) if b0 != b1)
     assert changes == nph * ndblk - 1
+
+
+@pytest.mark.parametrize("n,na,fp_expect,bp_expect,th_expect", [(256, 180, 2, 4, 16), (128, 90, 2, 2, 16), (384, 270, 2, 4, 16),
+                                                              (512, 360, 2, 2, 16), (768, 540, 1, 1, 32), (1024, 720, 1, 1, 32), (2048, 1800, 1, 1, 32)])
+def test_small_problems_are_split_over_clusters(n, na, fp_expect, bp_expect, th_expect):
+    """host-side choice of the cluster split (no CUDA involved): only geometries that would leave SMs idle are split,
+    every rank keeps at least two pipeline stages, and volumes from 768^2 up run unsplit"""
+    from whitomo_b200 import _capi
+    lib = _capi.load()
+    d = int(np.sqrt(2) * n + 1)
+    first = _plan(n, n, d, np.linspace(0, np.pi, na))[0]
+    fs, bs, th = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.wt_split_plan(n, n, d, na, len(first), ctypes.byref(fs), ctypes.byref(bs), ctypes.byref(th)) == 0
+    assert (fs.value, bs.value, th.value) == (fp_expect, bp_expect, th_expect)
+    assert lib.wt_split_plan(0, n, d, na, 1, None, None, None) == -1

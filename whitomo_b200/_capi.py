@@ -38,6 +38,7 @@ SIGNATURES = {
     "wt_step_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "wt_white_barrier_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_void_p, c_size_t, c_void_p]),
+    "wt_split_plan": (c_int, [c_int] * 5 + [ctypes.POINTER(c_int)] * 3),
     "wt_step_times": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
     "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),

@@ -128,7 +128,7 @@ template <class Epi>
 static int run_bp(const wt_geom *g, const float *sino, int n, int a_begin, int a_end, float *sp, const Epi &epi_proto,
                   cudaStream_t st, int row_begin = 0, int row_end = -1, bool packed = false) {
     BpParams p;
-    p.sp = sp; p.bwarp = g->d_bwarp; p.bwarpd = g->d_bwarpd;
+    p.sp = sp; p.bwarp = g->d_bwarp; p.bwarpd = g->d_bwarpd; p.plans = (const BpPlanRec *)g->d_bplans;
     p.R = g->rows; p.C = g->cols; p.A = g->nangles;
     p.padl = g->sino_padl; p.pitch = g->sino_pitch;
     p.a_begin = a_begin; p.a_end = a_end;
@@ -432,7 +432,7 @@ int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float
     padl = (padl + 3) & ~3;
     g->sino_padl = padl;
     g->sino_pitch = (padl + ndet + padl + BP_SEGW_MAX + 3) & ~3;
-    g->d_fp = nullptr; g->d_bp = nullptr; g->d_warp = nullptr; g->d_warpf = nullptr; g->d_bwarp = nullptr; g->d_bwarpd = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
+    g->d_fp = nullptr; g->d_bp = nullptr; g->d_warp = nullptr; g->d_warpf = nullptr; g->d_bwarp = nullptr; g->d_bwarpd = nullptr; g->d_bplans = nullptr; g->d_tiles = nullptr; g->d_order = nullptr;
     g->nphase = nphase;
     for (int i = 0; i <= FP_MAX_PHASES; ++i) g->phase_start[i] = phase_start[i];
     g->ntiles = (int)tiles.size();
@@ -456,6 +456,23 @@ int wt_geom_create_ex(int rows, int cols, int ndet, float det_width, const float
     if (e == cudaSuccess) e = cudaMemcpy(g->d_tiles, tiles.data(), sizeof(FpTile) * tiles.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_order, sizeof(int) * order.size());
     if (e == cudaSuccess) e = cudaMemcpy(g->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice);
+    // small geometries: K2's plans for every (tile, angle), computed once by the function the kernel otherwise runs inline
+    {
+        const int th = bp_tile_height(rows, cols);
+        const size_t ntx = (cols + BP_TW - 1) / BP_TW, nty = (rows + th - 1) / th;
+        const size_t bytes = ntx * nty * (size_t)nangles * sizeof(BpPlanRec);
+        static const int off = getenv("WT_NO_PLAN_TABLE") ? 1 : 0;      // A/B measurements
+        if (e == cudaSuccess && !off && bytes <= WT_BP_PLAN_TABLE_MAX) {
+            e = cudaMalloc(&g->d_bplans, bytes);
+            if (e == cudaSuccess) {
+                dim3 grid((unsigned)ntx, (unsigned)nty, (nangles + 127) / 128);
+                if (th == 16) bp_plan_table_kernel<16><<<grid, 128>>>(g->d_bwarp, g->d_bwarpd, padl, rows, cols, nangles, (BpPlanRec *)g->d_bplans);
+                else bp_plan_table_kernel<32><<<grid, 128>>>(g->d_bwarp, g->d_bwarpd, padl, rows, cols, nangles, (BpPlanRec *)g->d_bplans);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            }
+        }
+    }
     if (e != cudaSuccess) {
         wt_geom_destroy(g);
         return cuda_fail(e, "wt_geom_create");
@@ -472,6 +489,7 @@ void wt_geom_destroy(wt_geom *g) {
     if (g->d_warpf) cudaFree(g->d_warpf);
     if (g->d_bwarp) cudaFree(g->d_bwarp);
     if (g->d_bwarpd) cudaFree(g->d_bwarpd);
+    if (g->d_bplans) cudaFree(g->d_bplans);
     if (g->d_tiles) cudaFree(g->d_tiles);
     if (g->d_order) cudaFree(g->d_order);
     if (g->step_ev) {
@@ -511,6 +529,25 @@ int wt_geom_plan(int rows, int cols, int ndet, float det_width, const float *ang
     }
     return WT_OK;
 }
+
+int wt_split_plan(int rows, int cols, int ndet, int nangles, int n_tiles, int *fp_split, int *bp_split, int *bp_tile_rows) {
+    if (rows <= 0 || cols <= 0 || ndet <= 0 || nangles <= 0 || n_tiles <= 0) return invalid("wt_split_plan: non-positive size");
+    if (fp_split) *fp_split = fp_cluster_split(((ndet + FP_DT - 1) / FP_DT) * n_tiles, rows > cols ? rows : cols);
+    if (bp_split) *bp_split = bp_cluster_split(rows, cols, nangles);
+    if (bp_tile_rows) *bp_tile_rows = bp_tile_height(rows, cols);
+    return WT_OK;
+}
+
+#if WT_TRACE
+// development builds only (not in the header): copy the per-CTA time stamps of the last K1 (kernel 0) / K2 (kernel 1) launch
+int wt_debug_trace(int kernel, unsigned long long *out, int nctas) {
+    if (kernel < 0 || kernel > 1 || nctas > WT_TRACE_CTAS) return WT_ERR_INVALID;
+    cudaDeviceSynchronize();
+    WT_CUDA(cudaMemcpyFromSymbol(out, g_wt_trace, sizeof(unsigned long long) * WT_TRACE_POINTS * nctas,
+                                 sizeof(unsigned long long) * WT_TRACE_POINTS * WT_TRACE_CTAS * kernel));
+    return WT_OK;
+}
+#endif
 
 size_t wt_workspace_bytes(const wt_geom *g, int nimages) {
     if (!g || nimages <= 0) return 0;

@@ -59,6 +59,8 @@ struct BpParams {
     int row_begin, row_end;   // of those, the rows this launch computes (row_begin is a multiple of the tile height)
     int padl, pitch;
     int a_begin, a_end;
+    const struct BpPlanRec *plans;   // precomputed plans of a small geometry (bp_plan_table_kernel), or null
+    int csplit;       // CTAs of a cluster that share a tile, each taking a range of the angle blocks (1: no cluster)
 };
 
 // plain store: vol (n, R, C)
@@ -84,6 +86,9 @@ struct BpEpiStore {
 // on three taps it takes 22.0 ms (with selects on the taps instead: 23.2 ms at l1tex 89 %, issue 71 %; 2 / 3 / 4
 // shared pairs: 24.8 / 23.5 / 23.2 ms).  The float2 and float kernels (one or two images) are issue-bound to begin
 // with -- sharing costs them 7-12 % -- and keep separate taps.
+#ifndef WT_BP_ISSUE_UNIFORM
+#define WT_BP_ISSUE_UNIFORM 0
+#endif
 #ifndef WT_BP_NSHARE
 #define WT_BP_NSHARE 4
 #endif
@@ -112,6 +117,138 @@ struct BpSmem {
 //                pixel, so four candidate taps are weighted.  Every pixel is located on its own (the generic path).
 constexpr int BP_F_GENERIC = 1, BP_F_MIN = 2, BP_F_FOUR = 4, BP_F_KINK = 8;
 
+// What the consumers need to know about one angle of one tile (the producer's plan; 48 bytes)
+struct BpPlanRec {
+    float4 c4;     // affine piece A of d*: dcol, drow, base - 1/2;  Ah = A0 - B/2
+    float4 c5;     // affine piece B
+    float2 c6;     // B of piece A, flags (BP_F_*)
+    float bB;      // B of piece B
+    int aligned;   // first staged slot of the angle's packed sinogram row (a multiple of 4)
+};
+
+// Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
+//     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
+// The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two; over
+// positions [0, 64) G is replaced by its secant, common.cuh: BpWarpF), so z = G(k) - l * delta is affine over the
+// tile.  Ginv is piecewise affine in z with kinks where a ray STARTED on a binade boundary; the tile's z-range
+// (< 97 wide) usually holds none that matters (2-7 % of the tile x angle pairs at 8192^2 do): d* is then the max (or
+// min) of two affine pieces.  The stripe searches run in float on a 96-byte table per angle; only the pieces that
+// were picked are evaluated in double.
+// (tile origin (row0, col0), real extent tw x th pixels; `padl`: zero detectors in front of a packed sinogram row)
+__device__ __forceinline__ BpPlanRec bp_plan_angle(const BpWarpF *__restrict__ bwarp, const BpWarpD *__restrict__ bwarpd, int padl,
+                                                   int col0, int row0, int tw, int th, int a) {
+    BpPlanRec pl;
+    const BpWarpF *wf = bwarp + a;
+    const BpWarpD *w = bwarpd + a;
+    const bool vert = __ldg(&w->vertical) != 0;
+    const int k0 = vert ? col0 : row0, l0 = vert ? row0 : col0;
+    const int nk = vert ? tw : th, nl = vert ? th : tw;
+    const int ik = k0 < 64 ? 0 : min(WT_NM - 1, 26 - __clz(k0));      // floor(log2 k0) - 5
+    const float skf = __ldg(&wf->slope[ik]), iskf = __ldg(&wf->isl[ik]), dlf = __ldg(&wf->delta);
+    const float istep = __ldg(&wf->inv_step);
+    // z of the tile origin in double (the one quantity that needs it: d* to 1e-5 at |z| ~ 1e4) ...
+    const double za = __ldg(&w->cum[ik]) + (double)(k0 - (ik ? (32 << ik) : 0)) * __ldg(&w->slope[ik]) - (double)l0 * __ldg(&w->delta);
+    // ... the tile's extent and the stripe searches in float
+    const float zaf = (float)za, zk = skf * (float)(nk - 1), zl = -dlf * (float)(nl - 1);
+    const float zlo = zaf + fminf(0.0f, zk) + fminf(0.0f, zl), zhi = zaf + fmaxf(0.0f, zk) + fmaxf(0.0f, zl);
+    const float zc = 0.5f * (zlo + zhi), azc = fabsf(zc);
+    // piece A: the stripe of the tile centre (G's edges lie within 0.1 % of the powers of two, except beyond a
+    // stripe where the reference's rays stand still: walk from the power-of-two guess)
+    int ia = azc < 64.0f ? 0 : min(WT_NM - 1, (int)((__float_as_uint(azc) >> 23) & 0xffu) - 127 - 5);
+    while (ia > 0 && azc < __ldg(&wf->cum[ia])) --ia;
+    while (ia + 1 < WT_NM && azc >= __ldg(&wf->cum[ia + 1])) ++ia;
+    const bool negc = zc < 0.0f;
+    // piece B: across the kink inside (zlo, zhi) that bends d* most -- the edges of A's stripe on the centre's
+    // side of zero, and the first edge on the other side if the range straddles zero (a range is < 97 wide)
+    int ib = ia;
+    bool negb = negc, b_high = false;                                  // b_high: B lies at larger z than the centre
+    float worst = 5.0e-5f;                                             // kinks that bend d* by less are ignored
+    auto consider = [&](int m, bool neg) {
+        if (m < 1 || m >= WT_NM) return;
+        const float edge = __ldg(&wf->cum[m]), zb = neg ? -edge : edge;
+        const float far_side = zb > zc ? zhi - zb : zb - zlo;          // extent on the side away from the centre
+        const float w_ = __ldg(&wf->bend[m]) * far_side;
+        if (zb > zlo && zb < zhi && w_ > worst) {
+            worst = w_;
+            // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
+            const bool outward = neg ? (zb < zc) : (zb > zc);
+            ib = outward ? m : m - 1;
+            negb = neg;
+            b_high = zb > zc;
+        }
+    };
+    consider(ia, negc);
+    consider(ia + 1, negc);
+    if (ia == 0) consider(1, !negc);
+    const bool kink = !(ib == ia && negb == negc);
+    // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i;  d* at the tile origin in
+    // double, then relative to an integer near it in float; the slopes of d* in float
+    const double c0_base = __ldg(&w->c0_base), inv_step = __ldg(&w->inv_step);
+    auto origin = [&](bool neg, int i) {
+        const double pos = i ? (double)(32 << i) : 0.0, cum = __ldg(&w->cum[i]);
+        return ((neg ? -pos : pos) + (za - (neg ? -cum : cum)) * __ldg(&w->isl[i]) - c0_base) * inv_step - 0.5;
+    };
+    const double tA = origin(negc, ia);
+    const int ibase = __double2int_rd(tA);
+    const float islA = __ldg(&wf->isl[ia]), islB = __ldg(&wf->isl[ib]);
+    const float tAf = (float)(tA - (double)ibase), kA = skf * islA * istep, lA = -dlf * islA * istep;
+    float tBf = tAf, kB = kA, lB = lA;
+    if (kink) {
+        tBf = (float)(origin(negb, ib) - (double)ibase);
+        kB = skf * islB * istep;
+        lB = -dlf * islB * istep;
+    }
+    // beyond the kink piece B is the right one: d* = max(A, B) if B lies above A there, else min(A, B)
+    const float kf = (float)(nk - 1), lf = (float)(nl - 1);
+    bool use_max = true;
+    if (kink) {      // corner of the tile furthest into B's side in z
+        const float ck = (zk > 0.0f) == b_high ? kf : 0.0f, cl = (zl > 0.0f) == b_high ? lf : 0.0f;
+        use_max = (tBf + ck * kB + cl * lB) >= (tAf + ck * kA + cl * lA);
+    }
+    float dmin = 3.0e38f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float ck = (c & 1) ? kf : 0.0f, cl = (c & 2) ? lf : 0.0f;
+        const float va = tAf + ck * kA + cl * lA, vb = tBf + ck * kB + cl * lB;
+        dmin = fminf(dmin, use_max ? fmaxf(va, vb) : fminf(va, vb));
+    }
+    // B = len * |dc/dd| at fixed line: the rays' spacing on the pixel line, i.e. their spacing at the start
+    // stretched by the warp between the start stripe and the tile's stripe
+    const float a0 = __ldg(&wf->a0), bnom = __ldg(&wf->b);
+    const float bA = bnom * (__ldg(&wf->slope[ia]) * iskf), bB = kink ? bnom * (__ldg(&wf->slope[ib]) * iskf) : bA;
+    // rays closer than a position: a third ray can reach a pixel (weight up to len - B)
+    const bool four = fminf(bA, bB) < 0.9985f * a0;
+    const bool mild = !kink || fabsf(islA - islB) < 3.0e-4f * islA;
+    const bool generic = four || (kink && !mild);
+    const int flags = (generic ? BP_F_GENERIC : 0) | (kink && !generic ? BP_F_KINK : 0) | (kink && !use_max ? BP_F_MIN : 0) |
+                      (four ? BP_F_FOUR : 0);
+    // segment start (one slot of slack below the smallest d*: the shared pairs look one tap down)
+    const int lo = ibase + (int)floorf(dmin - 1.0e-3f) - (four ? 2 : 1) + padl;  // >= 0 by construction of padl
+    const int aligned = lo & ~3;
+    // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
+    // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
+    const float off = (float)(ibase + padl - aligned) - 0.5f;
+    pl.c4 = make_float4(vert ? kA : lA, vert ? lA : kA, tAf + off, a0 - 0.5f * bA);
+    pl.c5 = make_float4(vert ? kB : lB, vert ? lB : kB, tBf + off, a0 - 0.5f * bB);
+    pl.c6 = make_float2(bA, __int_as_float(flags));
+    pl.bB = bB;
+    pl.aligned = aligned;
+    return pl;
+}
+
+// Plans of a whole small geometry, computed once at geometry creation (the same function the kernel runs inline):
+// table[(tile_y * ntx + tile_x) * A + a].  For small problems the producer's plan -- ~370 dependent instructions with
+// four or five dependent table loads -- is the critical path of every pipeline stage.
+template <int TH>
+__global__ void bp_plan_table_kernel(const BpWarpF *bwarp, const BpWarpD *bwarpd, int padl, int R, int C, int A, BpPlanRec *table) {
+    const int a = blockIdx.z * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    const int col0 = blockIdx.x * BP_TW, row0 = blockIdx.y * TH;
+    table[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * A + a] =
+        bp_plan_angle(bwarp, bwarpd, padl, col0, row0, min(BP_TW, C - col0), min(TH, R - row0), a);
+}
+
+
 // Epilogues with kHasSums accumulate up to BP_MAX_SUMS per-thread sums (operator() gets a float* to them); the kernel
 // reduces them over the warp and hands them to epi.finish<W>(p, g, slot, nslots, sums): slot = (tile, warp), so the
 // partial sums are written in a fixed place and reduced in a fixed order by a later kernel (deterministic).
@@ -126,12 +263,26 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BpSmem<V, TH> &sm = *reinterpret_cast<BpSmem<V, TH> *>(smem_raw);
 
-    const int g = blockIdx.z;
+    // Small volumes (64 x 16 tiles, fewer tiles than SMs): the CTAs of a cluster share a tile, each backprojects a
+    // range of the angle blocks, and rank 0 adds the partial sums in rank order (through distributed shared memory)
+    // before the epilogue -- deterministic, and the epilogue still sees the complete sum.
+    constexpr bool SPLIT = TH == 16;
+    const int cs = SPLIT ? p.csplit : 1;
+    const int crank = cs > 1 ? (int)(blockIdx.z % (unsigned)cs) : 0;
+    const int g = cs > 1 ? (int)(blockIdx.z / (unsigned)cs) : (int)blockIdx.z;
+    int a_begin = p.a_begin, a_end = p.a_end;
+    if (cs > 1) {
+        const int per = ((a_end - a_begin + BP_AB - 1) / BP_AB + cs - 1) / cs * BP_AB;    // angles per rank, whole blocks
+        a_begin = min(a_end, a_begin + crank * per);
+        a_end = min(a_end, a_begin + per);
+    }
     const int col0 = blockIdx.x * BP_TW, row0 = p.row_begin + blockIdx.y * BP_TH;
     const int tw = min(BP_TW, p.C - col0), th = min(BP_TH, p.row_end - row0);  // real pixels of this tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nblk = (p.a_end - p.a_begin + BP_AB - 1) / BP_AB;
+    const int nblk = (a_end - a_begin + BP_AB - 1) / BP_AB;
 
+    WT_TRACE_POINT(1, 0, threadIdx.x == 0);
+    WT_TRACE_POINT(1, 1, threadIdx.x == 0);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < BP_STAGES; ++s) {
@@ -146,127 +297,39 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     // -- BEFORE the producer waits for the stage to be released, so the arithmetic is off the refill path -- and
     // issue() publishes them and starts the TMA copy of the angle's sinogram segment.
     //
-    // Detector coordinate of pixel (line l, position k), in the reference's arithmetic (common.cuh: WarpAngle):
-    //     d*(l, k) = (Ginv(G(k) - l * delta) - c0_base) / c0_step - 1/2.
-    // The tile lies inside one stripe of G (tiles are aligned to 64 columns / TH rows, stripes to powers of two; over
-    // positions [0, 64) G is replaced by its secant, common.cuh: BpWarpF), so z = G(k) - l * delta is affine over the
-    // tile.  Ginv is piecewise affine in z with kinks where a ray STARTED on a binade boundary; the tile's z-range
-    // (< 97 wide) usually holds none that matters (2-7 % of the tile x angle pairs at 8192^2 do): d* is then the max (or
-    // min) of two affine pieces.  The stripe searches run in float on a 96-byte table per angle; only the pieces that
-    // were picked are evaluated in double.
-    struct Plan { float4 c4, c5; float2 c6; float bB; const VecT *src; };
+    struct Plan { BpPlanRec r; const VecT *src; };
+    // (from the geometry's precomputed table when it has one -- small geometries, whole tiles of the unmirrored volume)
+    const bool tabled = p.plans != nullptr && p.Rproc == p.R && (p.row_end == p.R || p.row_end % BP_TH == 0);
+    const BpPlanRec *trow = p.plans + ((size_t)(row0 / BP_TH) * ((p.C + BP_TW - 1) / BP_TW) + blockIdx.x) * p.A;
     auto plan = [&](int blk) {
         Plan pl;
         pl.src = nullptr;
-        const int a = p.a_begin + blk * BP_AB + lane;
-        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        const int a = a_begin + blk * BP_AB + lane;
+        const int nvalid = min(BP_AB, a_end - (a_begin + blk * BP_AB));
         if (lane < nvalid) {
-            const BpWarpF *wf = p.bwarp + a;
-            const BpWarpD *w = p.bwarpd + a;
-            const bool vert = __ldg(&w->vertical) != 0;
-            const int k0 = vert ? col0 : row0, l0 = vert ? row0 : col0;
-            const int nk = vert ? tw : th, nl = vert ? th : tw;
-            const int ik = k0 < 64 ? 0 : min(WT_NM - 1, 26 - __clz(k0));      // floor(log2 k0) - 5
-            const float skf = __ldg(&wf->slope[ik]), iskf = __ldg(&wf->isl[ik]), dlf = __ldg(&wf->delta);
-            const float istep = __ldg(&wf->inv_step);
-            // z of the tile origin in double (the one quantity that needs it: d* to 1e-5 at |z| ~ 1e4) ...
-            const double za = __ldg(&w->cum[ik]) + (double)(k0 - (ik ? (32 << ik) : 0)) * __ldg(&w->slope[ik]) - (double)l0 * __ldg(&w->delta);
-            // ... the tile's extent and the stripe searches in float
-            const float zaf = (float)za, zk = skf * (float)(nk - 1), zl = -dlf * (float)(nl - 1);
-            const float zlo = zaf + fminf(0.0f, zk) + fminf(0.0f, zl), zhi = zaf + fmaxf(0.0f, zk) + fmaxf(0.0f, zl);
-            const float zc = 0.5f * (zlo + zhi), azc = fabsf(zc);
-            // piece A: the stripe of the tile centre (G's edges lie within 0.1 % of the powers of two, except beyond a
-            // stripe where the reference's rays stand still: walk from the power-of-two guess)
-            int ia = azc < 64.0f ? 0 : min(WT_NM - 1, (int)((__float_as_uint(azc) >> 23) & 0xffu) - 127 - 5);
-            while (ia > 0 && azc < __ldg(&wf->cum[ia])) --ia;
-            while (ia + 1 < WT_NM && azc >= __ldg(&wf->cum[ia + 1])) ++ia;
-            const bool negc = zc < 0.0f;
-            // piece B: across the kink inside (zlo, zhi) that bends d* most -- the edges of A's stripe on the centre's
-            // side of zero, and the first edge on the other side if the range straddles zero (a range is < 97 wide)
-            int ib = ia;
-            bool negb = negc, b_high = false;                                  // b_high: B lies at larger z than the centre
-            float worst = 5.0e-5f;                                             // kinks that bend d* by less are ignored
-            auto consider = [&](int m, bool neg) {
-                if (m < 1 || m >= WT_NM) return;
-                const float edge = __ldg(&wf->cum[m]), zb = neg ? -edge : edge;
-                const float far_side = zb > zc ? zhi - zb : zb - zlo;          // extent on the side away from the centre
-                const float w_ = __ldg(&wf->bend[m]) * far_side;
-                if (zb > zlo && zb < zhi && w_ > worst) {
-                    worst = w_;
-                    // the stripe on the far side of this kink (further from zero if the kink lies beyond the centre in |z|)
-                    const bool outward = neg ? (zb < zc) : (zb > zc);
-                    ib = outward ? m : m - 1;
-                    negb = neg;
-                    b_high = zb > zc;
-                }
-            };
-            consider(ia, negc);
-            consider(ia + 1, negc);
-            if (ia == 0) consider(1, !negc);
-            const bool kink = !(ib == ia && negb == negc);
-            // affine piece (sgn, i):  Ginv(z) = sgn * pos_i + (z - sgn * gcum_i) / slope_i;  d* at the tile origin in
-            // double, then relative to an integer near it in float; the slopes of d* in float
-            const double c0_base = __ldg(&w->c0_base), inv_step = __ldg(&w->inv_step);
-            auto origin = [&](bool neg, int i) {
-                const double pos = i ? (double)(32 << i) : 0.0, cum = __ldg(&w->cum[i]);
-                return ((neg ? -pos : pos) + (za - (neg ? -cum : cum)) * __ldg(&w->isl[i]) - c0_base) * inv_step - 0.5;
-            };
-            const double tA = origin(negc, ia);
-            const int ibase = __double2int_rd(tA);
-            const float islA = __ldg(&wf->isl[ia]), islB = __ldg(&wf->isl[ib]);
-            const float tAf = (float)(tA - (double)ibase), kA = skf * islA * istep, lA = -dlf * islA * istep;
-            float tBf = tAf, kB = kA, lB = lA;
-            if (kink) {
-                tBf = (float)(origin(negb, ib) - (double)ibase);
-                kB = skf * islB * istep;
-                lB = -dlf * islB * istep;
+            if (tabled) {
+                const float4 *q = reinterpret_cast<const float4 *>(trow + a);
+                const float4 q2 = __ldg(q + 2);
+                pl.r.c4 = __ldg(q);
+                pl.r.c5 = __ldg(q + 1);
+                pl.r.c6 = make_float2(q2.x, q2.y);
+                pl.r.bB = q2.z;
+                pl.r.aligned = __float_as_int(q2.w);
+            } else {
+                pl.r = bp_plan_angle(p.bwarp, p.bwarpd, p.padl, col0, row0, tw, th, a);
             }
-            // beyond the kink piece B is the right one: d* = max(A, B) if B lies above A there, else min(A, B)
-            const float kf = (float)(nk - 1), lf = (float)(nl - 1);
-            bool use_max = true;
-            if (kink) {      // corner of the tile furthest into B's side in z
-                const float ck = (zk > 0.0f) == b_high ? kf : 0.0f, cl = (zl > 0.0f) == b_high ? lf : 0.0f;
-                use_max = (tBf + ck * kB + cl * lB) >= (tAf + ck * kA + cl * lA);
-            }
-            float dmin = 3.0e38f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float ck = (c & 1) ? kf : 0.0f, cl = (c & 2) ? lf : 0.0f;
-                const float va = tAf + ck * kA + cl * lA, vb = tBf + ck * kB + cl * lB;
-                dmin = fminf(dmin, use_max ? fmaxf(va, vb) : fminf(va, vb));
-            }
-            // B = len * |dc/dd| at fixed line: the rays' spacing on the pixel line, i.e. their spacing at the start
-            // stretched by the warp between the start stripe and the tile's stripe
-            const float a0 = __ldg(&wf->a0), bnom = __ldg(&wf->b);
-            const float bA = bnom * (__ldg(&wf->slope[ia]) * iskf), bB = kink ? bnom * (__ldg(&wf->slope[ib]) * iskf) : bA;
-            // rays closer than a position: a third ray can reach a pixel (weight up to len - B)
-            const bool four = fminf(bA, bB) < 0.9985f * a0;
-            const bool mild = !kink || fabsf(islA - islB) < 3.0e-4f * islA;
-            const bool generic = four || (kink && !mild);
-            const int flags = (generic ? BP_F_GENERIC : 0) | (kink && !generic ? BP_F_KINK : 0) | (kink && !use_max ? BP_F_MIN : 0) |
-                              (four ? BP_F_FOUR : 0);
-            // segment start (one slot of slack below the smallest d*: the shared pairs look one tap down)
-            const int lo = ibase + (int)floorf(dmin - 1.0e-3f) - (four ? 2 : 1) + p.padl;  // >= 0 by construction of padl
-            const int aligned = lo & ~3;
-            // base is d* - 1/2 relative to the segment start; with f' = frac - 1/2 both tap weights share one
-            // constant: w0 = max(0, Ah - B f'), w1 = max(0, Ah + B f'), Ah = A0 - B/2 (= A1 + B/2)
-            const float off = (float)(ibase + p.padl - aligned) - 0.5f;
-            pl.c4 = make_float4(vert ? kA : lA, vert ? lA : kA, tAf + off, a0 - 0.5f * bA);
-            pl.c5 = make_float4(vert ? kB : lB, vert ? lB : kB, tBf + off, a0 - 0.5f * bB);
-            pl.c6 = make_float2(bA, __int_as_float(flags));
-            pl.bB = bB;
-            pl.src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + aligned;
+            pl.src = reinterpret_cast<const VecT *>(p.sp) + ((size_t)g * p.A + a) * p.pitch + pl.r.aligned;
         }
         return pl;
     };
     auto issue = [&](int blk, const Plan &pl) {
         const int s = blk % BP_STAGES;
-        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        const int nvalid = min(BP_AB, a_end - (a_begin + blk * BP_AB));
         if (lane < nvalid) {
-            sm.cst[s][lane] = pl.c4;
-            sm.cst2[s][lane] = pl.c5;
-            sm.cst3[s][lane] = pl.c6;
-            sm.cst4[s][lane] = pl.bB;
+            sm.cst[s][lane] = pl.r.c4;
+            sm.cst2[s][lane] = pl.r.c5;
+            sm.cst3[s][lane] = pl.r.c6;
+            sm.cst4[s][lane] = pl.r.bB;
         }
         __syncwarp();
         if (lane == 0) {
@@ -274,7 +337,19 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
         }
         __syncwarp();
+#if WT_BP_ISSUE_UNIFORM
+        // one lane issues the stage's copies from broadcast addresses: per-lane copies compile to an elect / R2UR loop
+        // that serialises the lanes at ~150 cycles per copy (1.2 us per stage -- the critical path of small problems)
+        const unsigned long long mine = (unsigned long long)pl.src;
+#pragma unroll
+        for (int k = 0; k < BP_AB; ++k) {
+            const unsigned long long sk = __shfl_sync(0xffffffffu, mine, k);
+            if (lane == 0 && k < nvalid)
+                tma_load_1d(&sm.seg[s][k][0], reinterpret_cast<const void *>(sk), (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
+        }
+#else
         if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], pl.src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
+#endif
     };
 
     if (warp == BP_THREADS / 32) {
@@ -284,8 +359,10 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             if (blk >= BP_STAGES) mbar_wait(&sm.empty[blk % BP_STAGES], (uint32_t)(((blk / BP_STAGES) - 1) & 1));
             issue(blk, pl);
         }
+        if (cs > 1) cluster_sync_all();     // (the consumers' one, below)
         return;
     }
+    WT_TRACE_POINT(1, 2, threadIdx.x == 0);
 
     // this thread's pixels: columns lane, lane+32; rows in vertically adjacent pairs 2*warp + 16*j + {0, 1} (clamped
     // into the real tile so that every smem index stays inside the staged segment; clamped results are dropped)
@@ -416,7 +493,8 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
     for (int blk = 0; blk < nblk; ++blk) {
         const int s = blk % BP_STAGES;
         mbar_wait(&sm.full[s], (uint32_t)((blk / BP_STAGES) & 1));
-        const int nvalid = min(BP_AB, p.a_end - (p.a_begin + blk * BP_AB));
+        WT_TRACE_POINT(1, 3, threadIdx.x == 0 && blk == 0);
+        const int nvalid = min(BP_AB, a_end - (a_begin + blk * BP_AB));
         for (int k = 0; k < nvalid; ++k) {
             const float4 c4 = sm.cst[s][k];
             const float2 c6 = sm.cst3[s][k];
@@ -435,6 +513,33 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with stage s
+    }
+
+    WT_TRACE_POINT(1, 4, threadIdx.x == 0);
+    if (cs > 1) {
+        // partial sums of ranks 1 .. cs-1 travel to rank 0's shared memory: part[rank - 1][accumulator][thread]
+        float *part = reinterpret_cast<float *>(smem_raw + sizeof(BpSmem<V, TH>));
+        constexpr int NACC = BP_RPT * 2 * V;
+        if (crank > 0) {
+#pragma unroll
+            for (int r = 0; r < BP_RPT; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        st_cluster_f32(part + ((size_t)(crank - 1) * NACC + (r * 2 + c) * V + i) * BP_THREADS + threadIdx.x, 0, acc[r][c][i]);
+        }
+        cluster_sync_all();
+        WT_TRACE_POINT(1, 5, threadIdx.x == 0);
+        if (crank > 0) return;
+        for (int k = 1; k < cs; ++k)
+#pragma unroll
+            for (int r = 0; r < BP_RPT; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < V; ++i)
+                        acc[r][c][i] += part[((size_t)(k - 1) * NACC + (r * 2 + c) * V + i) * BP_THREADS + threadIdx.x];
     }
 
     float sums[BP_MAX_SUMS];
@@ -464,6 +569,8 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             }
         }
     }
+    WT_TRACE_POINT(1, 6, threadIdx.x == 0);
+    WT_TRACE_POINT(1, 7, threadIdx.x == 0);
     if constexpr (Epi::kHasSums && !MIRROR) {
 #pragma unroll
         for (int q = 0; q < BP_MAX_SUMS; ++q) sums[q] = warp_sum(sums[q]);
@@ -482,20 +589,53 @@ inline int bp_tile_height(int rows, int cols) {
     return tiles32 <= 148 ? 16 : 32;
 }
 
+// Cluster split of the angle blocks (bp_kernel): only for volumes whose 64 x 16 tiles leave SMs idle (up to four CTAs
+// per SM after the split), as long as every rank keeps at least two angle blocks -- measured on the C-side SIRT loop:
+// 256^2 75 -> 39 us (4 ranks), 384^2 130 -> 95 us, 512^2 191 -> 161 us (2 ranks) per iteration.  Like the tile height it
+// depends on the geometry alone, never on the number of images or on the epilogue, so an image's bits do not depend on
+// the call it travels in.
+constexpr int BP_MAX_SPLIT = 8;
+inline int bp_cluster_split(int rows, int cols, int nangles) {
+    if (bp_tile_height(rows, cols) != 16) return 1;
+    static const int off = getenv("WT_NO_SPLIT") ? 1 : 0;       // A/B measurements
+    if (off) return 1;
+    static const int forced = getenv("WT_BP_SPLIT") ? atoi(getenv("WT_BP_SPLIT")) : 0;
+    if (forced >= 1 && forced <= BP_MAX_SPLIT) return forced;
+    const long tiles = (long)((cols + BP_TW - 1) / BP_TW) * ((rows + 15) / 16);
+    const int nblk = (nangles + BP_AB - 1) / BP_AB;
+    int cs = 1;
+    while (cs < 4 && tiles * cs * 2 <= 4 * 148 && nblk >= 4 * cs) cs *= 2;
+    return cs;
+}
+
 template <int V, class Epi, bool MIRROR, int TH>
 inline cudaError_t launch_bp_th(const BpParams &p, const Epi &epi, int groups, cudaStream_t st) {
-    const size_t smem = sizeof(BpSmem<V, TH>);
+    // cluster split (64 x 16 tiles only): rank 0 receives the other ranks' accumulators behind the pipeline buffers
+    constexpr size_t part_bytes = (size_t)BpTile<TH>::RPT * 2 * V * BP_THREADS * sizeof(float);
+    const int cs = TH == 16 ? bp_cluster_split(p.R, p.C, p.A) : 1;
+    const size_t smem_max = sizeof(BpSmem<V, TH>) + (TH == 16 ? (BP_MAX_SPLIT - 1) * part_bytes : 0);
+    const size_t smem = sizeof(BpSmem<V, TH>) + (cs - 1) * part_bytes;
     static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi, MIRROR, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bp_kernel<V, Epi, MIRROR, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.row_end - p.row_begin + TH - 1) / TH, groups);
-    bp_kernel<V, Epi, MIRROR, TH><<<grid, BP_BLOCK, smem, st>>>(p, epi);
-    return cudaSuccess;
+    BpParams q = p;
+    q.csplit = cs;
+    dim3 grid((p.C + BP_TW - 1) / BP_TW, (p.row_end - p.row_begin + TH - 1) / TH, groups * cs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(BP_BLOCK);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    LaunchAttrs la;
+    if (cs > 1) la.cluster(1, 1, cs);
+    cfg.attrs = la.at;
+    cfg.numAttrs = la.n;
+    return cudaLaunchKernelEx(&cfg, bp_kernel<V, Epi, MIRROR, TH>, q, epi);
 }
 
 template <int V, class Epi, bool MIRROR = false>

@@ -1,6 +1,7 @@
 // Shared device helpers and the geometry handle of the whitomo_b200 engine (sm_100a only).
 #pragma once
-#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cuda.h>
+#include <cstdlib>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -35,6 +36,7 @@ template <int TH> struct BpTile {
     static constexpr int SEGW = TH >= 32 ? 80 : 72;
 };
 constexpr int BP_SEGW_MAX = 80;
+constexpr size_t WT_BP_PLAN_TABLE_MAX = 8u << 20;   // bytes of precomputed K2 plans a geometry may own (bp.cuh: BpPlanRec)
 constexpr int BP_THREADS = 256;            // consumer threads
 constexpr int BP_BLOCK = BP_THREADS + 32;  // + one producer warp that only drives the TMA pipeline
 
@@ -149,6 +151,7 @@ struct wt_geom {
     wt::WarpAngleF *d_warpf; // float copy for K1
     wt::BpWarpF *d_bwarp;    // merged float view for K2
     wt::BpWarpD *d_bwarpd;   // ... and its double version
+    void *d_bplans;          // wt::BpPlanRec[tiles][nangles]: K2's per-(tile, angle) plans, small geometries only (else null)
     int positions;           // WT_POS_ASTRA | WT_POS_EXACT
     void *d_tiles;   // wt::FpTile[ntiles]: angle tiles of the forward projector
     int ntiles;
@@ -304,6 +307,50 @@ __device__ __forceinline__ void tma_load_tile_3d(void *smem_dst, const CUtensorM
                      smem_u32(smem_dst)),
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
+}
+// ---- development aid (-DWT_TRACE=1 builds only; tools/trace_small.py): per-CTA time stamps of K1 / K2 ----
+#ifndef WT_TRACE
+#define WT_TRACE 0
+#endif
+#if WT_TRACE
+constexpr int WT_TRACE_CTAS = 2048, WT_TRACE_POINTS = 8;
+__device__ unsigned long long g_wt_trace[2][WT_TRACE_CTAS][WT_TRACE_POINTS];   // [kernel][linear CTA][point]: point 0 = globaltimer (ns), others clock64
+__device__ __forceinline__ void wt_trace_point(int kernel, int point) {
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta >= (unsigned)WT_TRACE_CTAS) return;
+    unsigned long long t;
+    if (point == 0 || point == WT_TRACE_POINTS - 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = clock64();
+    g_wt_trace[kernel][cta][point] = t;
+}
+#define WT_TRACE_POINT(kernel, point, cond) do { if (cond) wt::wt_trace_point(kernel, point); } while (0)
+#else
+#define WT_TRACE_POINT(kernel, point, cond) do { } while (0)
+#endif
+
+// launch attributes of K1 / K2: the optional cluster dimension.  (Programmatic dependent launch -- letting a kernel's
+// set-up overlap the previous kernel's tail -- was built and measured in round 2: the CTAs did start early and wait, but
+// neither the 256^2 SIRT loop (25.15k vs 25.16k iterations/s) nor the C4 step changed; removed.)
+struct LaunchAttrs {
+    cudaLaunchAttribute at[1];
+    int n = 0;
+    void cluster(int x, int y, int z) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = x; at[n].val.clusterDim.y = y; at[n].val.clusterDim.z = z;
+        ++n;
+    }
+};
+
+// ---- thread-block clusters: small problems split a tile's angles (K2) / lines (K1) over the CTAs of a cluster ----
+// All threads of all CTAs of the cluster that have not exited: release their writes (remote ones included), wait, acquire.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the shared memory of CTA `rank` of the cluster, at the address `local` has in this CTA
+__device__ __forceinline__ void st_cluster_f32(const float *local, uint32_t rank, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -143,6 +143,7 @@ struct FpParams {
     int nphase;
     int phase_start[FP_MAX_PHASES + 1];  // prefix offsets into `order`
     int ndblk;         // detector blocks per tile
+    int csplit;        // CTAs of a cluster that share a (tile, detector block), each taking a range of the line chunks (1: none)
 };
 
 // Launch order.  The grid is linear in x: phase by phase (vertical angles read VN, horizontal angles VT), inside a
@@ -157,7 +158,7 @@ struct FpParams {
 struct FpBlock { int tile, dblk; };
 __device__ __forceinline__ FpBlock fp_block(const FpParams &p) {
     // static indices only: a dynamically indexed kernel-parameter array would be copied to local memory
-    const int lin0 = blockIdx.x;
+    const int lin0 = p.csplit > 1 ? (int)(blockIdx.x / (unsigned)p.csplit) : (int)blockIdx.x;
     if (p.nphase == 0) {   // tile-major, detector blocks fastest (WT_FP_ORDER=tile, kept for A/B measurements)
         FpBlock b;
         b.tile = lin0 / p.ndblk;
@@ -256,6 +257,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
     const int pitch = fp_pitch(npos);
     const VecT *base = reinterpret_cast<const VecT *>(an0.vertical ? p.vn : p.vt) + (size_t)g * nlines * pitch;
 
+    WT_TRACE_POINT(0, 0, tid == 0);
+    WT_TRACE_POINT(0, 1, tid == 0);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < FP_STAGES; ++s) {
@@ -330,15 +333,27 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         if (!valid || l_hi <= l_lo) l_lo = l_hi = 0;    // (a ray that misses the volume has nothing to skip to either)
     }
     __syncthreads();
+    WT_TRACE_POINT(0, 2, tid == 0);
     const int Lb = sm.lo, Le = sm.hi;
     const bool tile_in_range = tile.first < p.a_end && tile.first + tile.count > p.a_begin;   // CTA-uniform
-    const int nchunk = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
+    const int nchunk_all = (tile_in_range && Le > Lb) ? (Le - Lb + FP_LB - 1) / FP_LB : 0;
+    // Small problems (fewer CTAs than the SMs hold): the CTAs of a cluster share the rays, each walks a range of the line
+    // chunks, and rank 0 adds the partial ray sums in rank order before the epilogue (deterministic; the epilogue sees
+    // the complete sum).  `ch0`: this rank's first chunk.
+    const int cs = p.csplit;
+    const int crank = cs > 1 ? (int)(blockIdx.x % (unsigned)cs) : 0;
+    int ch0 = 0, nchunk = nchunk_all;
+    if (cs > 1) {
+        const int per = (nchunk_all + cs - 1) / cs;
+        ch0 = min(nchunk_all, crank * per);
+        nchunk = min(nchunk_all, ch0 + per) - ch0;
+    }
 
     // producer warp: where the window of chunk `ch` (the ch-th chunk of FP_LB lines, ascending: the reference's
     // summation order) starts -- computed BEFORE the producer waits for the stage to be released
     int stripe = 0;          // producer lanes: stripe of the lane's angle at the last planned chunk
     auto plan = [&](int ch) {
-        const int l0 = Lb + ch * FP_LB;
+        const int l0 = Lb + (ch0 + ch) * FP_LB;
         const int l1 = min(l0 + FP_LB, nlines) - 1;
         // left-most position any ray of the tile takes on these lines (monotone in l: attained at an end)
         float m = 3.0e38f;
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
     };
     auto issue = [&](int ch, int ws) {
         const int s = ch % FP_STAGES;
-        const int l0 = Lb + ch * FP_LB;
+        const int l0 = Lb + (ch0 + ch) * FP_LB;
         const int nl = min(l0 + FP_LB, nlines) - l0;
         if (lane == 0) {
             fence_proxy_async();                     // consumers' generic-proxy reads of this stage precede the refill
@@ -402,13 +417,15 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         // the reference's running sum: c at line l is c_0 after l float32 additions of delta.  Lines before the ray
         // enters the volume are skipped by doing just the additions.
         if (nchunk > 0) {
+            const int lskip = min(l_hi, max(l_lo, Lb + ch0 * FP_LB));      // (a later rank of a cluster starts further down)
 #pragma unroll 8
-            for (int l = 0; l < l_lo; ++l) c_run += delta;
+            for (int l = 0; l < lskip; ++l) c_run += delta;
         }
         for (int ch = 0; ch < nchunk; ++ch) {
             const int s = ch % FP_STAGES;
             mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
-            const int l0 = Lb + ch * FP_LB;
+            WT_TRACE_POINT(0, 3, tid == 0 && ch == 0);
+            const int l0 = Lb + (ch0 + ch) * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
             if (la < lb) {
                 // c - 1/2 relative to the window start: window starts are integers, so the difference of two float32
@@ -438,7 +455,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         for (int ch = 0; ch < nchunk; ++ch) {
             const int s = ch % FP_STAGES;
             mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
-            const int l0 = Lb + ch * FP_LB;
+            const int l0 = Lb + (ch0 + ch) * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
             if (la < lb) {
                 // c - 0.5 relative to the window start at line la; then one FADD per line
@@ -464,6 +481,23 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         }
     }
 
+    WT_TRACE_POINT(0, 4, tid == 0);
+    if (cs > 1) {
+        // partial ray sums of ranks 1 .. cs-1 travel to rank 0's shared memory: part[rank - 1][component][thread]
+        float *part = reinterpret_cast<float *>(smem_raw + sizeof(FpSmem<V>));
+        if (crank > 0 && !producer) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) st_cluster_f32(part + ((crank - 1) * V + i) * FP_THREADS + tid, 0, acc[i]);
+        }
+        cluster_sync_all();
+        WT_TRACE_POINT(0, 5, tid == 0);
+        if (crank > 0) return;
+        if (!producer)
+            for (int k = 1; k < cs; ++k)
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[i] += part[((k - 1) * V + i) * FP_THREADS + tid];
+    }
+
     // the staging buffers are free now: epilogues may use them as CTA scratch (after their own __syncthreads)
     float *scratch = reinterpret_cast<float *>(&sm.seg[0][0][0]);
     if constexpr (MIRROR) {
@@ -480,6 +514,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         for (int i = 0; i < V; ++i) val[i] = acc[i] * len;
         epi.template operator()<V>(p, g, a, d, valid, val, scratch, 0, 1);
     }
+    WT_TRACE_POINT(0, 6, tid == 0);
+    WT_TRACE_POINT(0, 7, tid == 0);
 }
 
 // Tensor map of one packed copy (G groups x nlines lines x pitch positions x V floats) as a rank-2 tensor (position, line)
@@ -509,19 +545,38 @@ inline cudaError_t fp_tensor_map(CUtensorMap *tm, const float *packed, int V, in
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Cluster split of the line chunks (fp_kernel): two CTAs per (tile, detector block) when there are at most about two
+// waves of them (4 CTAs per SM) and every rank keeps at least four chunks -- measured on the C-side SIRT loop: 256^2
+// 52 -> 39 us, 384^2 95 -> 88 us, 512^2 161 -> 156 us per iteration; slower from 768^2 on (tools/split_probe*.sh).  It
+// depends on the geometry alone -- never on the number of images, the angle range or the epilogue -- so a ray's bits do
+// not depend on the call it travels in.
+constexpr int FP_MAX_SPLIT = 8;
+inline int fp_cluster_split(int blocks, int nlines_max) {
+    static const int off = getenv("WT_NO_SPLIT") ? 1 : 0;       // A/B measurements
+    if (off) return 1;
+    static const int forced = getenv("WT_FP_SPLIT") ? atoi(getenv("WT_FP_SPLIT")) : 0;
+    if (forced >= 1 && forced <= FP_MAX_SPLIT) return forced;
+    const int nchunk = (nlines_max + FP_LB - 1) / FP_LB;
+    return (blocks <= 1200 && nchunk >= 8) ? 2 : 1;
+}
+
 template <int V, class Epi, bool MIRROR = false>
 inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cudaStream_t st) {
-    const size_t smem = sizeof(FpSmem<V>);
+    FpParams q = p;
+    q.ndblk = (p.Dproc + FP_DT - 1) / FP_DT;
+    constexpr size_t part_bytes = (size_t)V * FP_THREADS * sizeof(float);
+    const int cs = fp_cluster_split(q.ndblk * p.ntiles, max(p.R, p.C));
+    q.csplit = cs;
+    const size_t smem = sizeof(FpSmem<V>) + (cs - 1) * part_bytes;
     static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fp_kernel<V, Epi, MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(FpSmem<V>) + (FP_MAX_SPLIT - 1) * part_bytes));
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    FpParams q = p;
-    q.ndblk = (p.Dproc + FP_DT - 1) / FP_DT;
     // tensor maps of the two packed copies (host-side encoding of a few hundred bytes; they travel as kernel parameters)
     alignas(64) CUtensorMap tm_vn, tm_vt;
     memset(&tm_vn, 0, sizeof(tm_vn));
@@ -531,9 +586,17 @@ inline cudaError_t launch_fp(const FpParams &p, const Epi &epi, int groups, cuda
         if (e == cudaSuccess) e = fp_tensor_map(&tm_vt, p.vt, V, fp_pitch(p.R), (size_t)groups * p.C);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(q.ndblk * p.ntiles, 1, groups);
-    fp_kernel<V, Epi, MIRROR><<<grid, FP_BLOCK, smem, st>>>(q, epi, tm_vn, tm_vt);
-    return cudaSuccess;
+    dim3 grid(q.ndblk * p.ntiles * cs, 1, groups);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FP_BLOCK);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    LaunchAttrs la;
+    if (cs > 1) la.cluster(cs, 1, 1);
+    cfg.attrs = la.at;
+    cfg.numAttrs = la.n;
+    return cudaLaunchKernelEx(&cfg, fp_kernel<V, Epi, MIRROR>, q, epi, tm_vn, tm_vt);
 }
 
 }  // namespace wt
