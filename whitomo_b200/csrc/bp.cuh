@@ -86,9 +86,6 @@ struct BpEpiStore {
 // on three taps it takes 22.0 ms (with selects on the taps instead: 23.2 ms at l1tex 89 %, issue 71 %; 2 / 3 / 4
 // shared pairs: 24.8 / 23.5 / 23.2 ms).  The float2 and float kernels (one or two images) are issue-bound to begin
 // with -- sharing costs them 7-12 % -- and keep separate taps.
-#ifndef WT_BP_ISSUE_UNIFORM
-#define WT_BP_ISSUE_UNIFORM 0
-#endif
 #ifndef WT_BP_NSHARE
 #define WT_BP_NSHARE 4
 #endif
@@ -337,19 +334,10 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(nvalid * BP_SEGW * sizeof(VecT)));
         }
         __syncwarp();
-#if WT_BP_ISSUE_UNIFORM
-        // one lane issues the stage's copies from broadcast addresses: per-lane copies compile to an elect / R2UR loop
-        // that serialises the lanes at ~150 cycles per copy (1.2 us per stage -- the critical path of small problems)
-        const unsigned long long mine = (unsigned long long)pl.src;
-#pragma unroll
-        for (int k = 0; k < BP_AB; ++k) {
-            const unsigned long long sk = __shfl_sync(0xffffffffu, mine, k);
-            if (lane == 0 && k < nvalid)
-                tma_load_1d(&sm.seg[s][k][0], reinterpret_cast<const void *>(sk), (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
-        }
-#else
+        // (per-lane copies compile to an elect / R2UR loop, ~150 cycles per copy; one lane issuing the 16 copies from
+        // shuffled addresses compiles to 16 such one-trip loops and measured no faster: 23.29 vs 23.15 ms at C4, 39.0 vs
+        // 38.7 us per 256^2 SIRT iteration)
         if (lane < nvalid) tma_load_1d(&sm.seg[s][lane][0], pl.src, (uint32_t)(BP_SEGW * sizeof(VecT)), &sm.full[s]);
-#endif
     };
 
     if (warp == BP_THREADS / 32) {

@@ -199,14 +199,14 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
     if fused:       # three launches per iteration (K2 + step, K1, reduction), see white_barrier_stack
         state = proj.new_step_state(spectrum, S)
         f_loss, _ = proj.white_barrier_step(spectrum, c, meas, state, init=True)
+    f_hist, r_hist = [], []             # per iteration: f (S,) float64 and ||c0 c1|| (S,); combined after the loop
     for it in range(start_iter, start_iter + n_iters):
         if not fused:
             _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
             g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
-        reg_loss = 0.0
+        f_hist.append(f_loss)
         if dissimilarity_constraint and K == 2:
-            reg_loss = torch.linalg.vector_norm((beta_reg * c[:, 0] * c[:, 1]).reshape(S, -1), dim=1).double()
-        losses.append(torch.sqrt(2.0 * f_loss) + reg_loss)
+            r_hist.append(torch.linalg.vector_norm((c[:, 0] * c[:, 1]).reshape(S, -1), dim=1))
         mask = 0xFFFFFFFF
         if alternate and K == 2:
             mask = 0b01 if it % 4 == 0 else 0b10
@@ -215,6 +215,12 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
                                                 triv_w=triv_w, mode=mode, elem_mask=mask)
         else:
             proj.barrier_update(c, g, alpha, beta_reg, 0.0, reg_w=reg_w, triv_w=triv_w, mode=mode, elem_mask=mask)
+    # losses[i] = ||q_i|| + ||beta c0 c1||: two small kernels per iteration inside the loop, the rest once here
+    if f_hist:
+        total = torch.sqrt(2.0 * torch.stack(f_hist))
+        if r_hist:
+            total = total + abs(beta_reg) * torch.stack(r_hist).double()
+        losses = list(total.unbind(0))
     return c, losses
 
 
