@@ -344,6 +344,7 @@ struct LaunchAttrs {
 // ---- thread-block clusters: small problems split a tile's angles (K2) / lines (K1) over the CTAs of a cluster ----
 // All threads of all CTAs of the cluster that have not exited: release their writes (remote ones included), wait, acquire.
 __device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();      // (.aligned: the warp must arrive converged)
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // store into the shared memory of CTA `rank` of the cluster, at the address `local` has in this CTA
