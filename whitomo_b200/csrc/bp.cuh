@@ -89,6 +89,9 @@ struct BpEpiStore {
 #ifndef WT_BP_NSHARE
 #define WT_BP_NSHARE 4
 #endif
+#ifndef WT_BP_PAIRPIX
+#define WT_BP_PAIRPIX 1      // float / float2 kernels: two pixels per pass through the packed fp32 pipe (bp_kernel: pixel_pair)
+#endif
 template <int V> struct BpShare { static constexpr int value = V >= 4 ? WT_BP_NSHARE : 0; };
 // tile row of a consumer thread's r-th pixel row: vertically adjacent pairs 2*warp + {0, 1}, then 16 rows further down
 __host__ __device__ constexpr int bp_row_of(int warp, int r) { return 2 * warp + 16 * (r >> 1) + (r & 1); }
@@ -388,6 +391,36 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
         unpack<V>(tap[1], v1);
         tap_pair_fma<V>(w0, v0, w1, v1, a);
     };
+    // Two pixels at once (float and float2 kernels, which are bound by the instruction issue rate: ~14 issue slots per
+    // pixel and angle): cell, fraction and weights of both go through the packed fp32 pipe (FADD2 / FFMA2, each half
+    // rounded like the scalar operation; x - y is written fma(y, -1, x), whose product is exact), and with one image per
+    // position so do the tap FMAs -- the bits of `single`, ~9 slots per pixel.
+    auto pixel_pair = [&](float2 ds, const float4 &c4, float bw, const VecT *seg, float (&a0)[V], float (&a1)[V]) {
+        const float2 t = __fadd2_rn(ds, make_float2(MAGIC, MAGIC));
+        const float2 u = __fadd2_rn(t, make_float2(-MAGIC, -MAGIC));
+        const float2 f = __ffma2_rn(u, make_float2(-1.0f, -1.0f), ds);      // frac(d*) - 1/2
+        check_index(__float_as_int(t.x) - MAGIC_BITS, __float_as_int(t.x) - MAGIC_BITS + 1, BP_SEGW);
+        check_index(__float_as_int(t.y) - MAGIC_BITS, __float_as_int(t.y) - MAGIC_BITS + 1, BP_SEGW);
+        const VecT *ta = (seg - MAGIC_BITS) + __float_as_int(t.x), *tb = (seg - MAGIC_BITS) + __float_as_int(t.y);
+        float2 w0 = __ffma2_rn(f, make_float2(-bw, -bw), make_float2(c4.w, c4.w));
+        float2 w1 = __ffma2_rn(f, make_float2(bw, bw), make_float2(c4.w, c4.w));
+        w0.x = fmaxf(0.0f, w0.x); w0.y = fmaxf(0.0f, w0.y);
+        w1.x = fmaxf(0.0f, w1.x); w1.y = fmaxf(0.0f, w1.y);
+        float va0[V], va1[V], vb0[V], vb1[V];
+        unpack<V>(ta[0], va0);
+        unpack<V>(ta[1], va1);
+        unpack<V>(tb[0], vb0);
+        unpack<V>(tb[1], vb1);
+        if constexpr (V == 1) {
+            float2 s2 = make_float2(a0[0], a1[0]);
+            s2 = __ffma2_rn(w0, make_float2(va0[0], vb0[0]), __ffma2_rn(w1, make_float2(va1[0], vb1[0]), s2));
+            a0[0] = s2.x;
+            a1[0] = s2.y;
+        } else {
+            tap_pair_fma<V>(w0.x, va0, w1.x, va1, a0);
+            tap_pair_fma<V>(w0.y, vb0, w1.y, vb1, a1);
+        }
+    };
     // A vertically adjacent pixel pair with shared taps (float4 kernels).  The upper pixel is located as `single`
     // does; the lower one sits drow (|drow| <= 1) detectors further, so its cell is the same one or the next one in
     // the direction of drow and its fraction follows with one add and one compare -- no second round trip through the
@@ -430,18 +463,28 @@ __global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
             const float b = fmaf(j, c5.x, fmaf(i, c5.y, c5.z));
             return use_min ? fminf(a, b) : fmaxf(a, b);
         };
+        if constexpr (!KINK && BpShare<V>::value == 0 && WT_BP_PAIRPIX) {
 #pragma unroll
-        for (int j = 0; j < BP_RPT / 2; ++j) {
-            const float dr0 = fmaf(ir[2 * j], c4.y, c4.z), dr0b = KINK ? fmaf(ir[2 * j], c5.y, c5.z) : 0.0f;
+            for (int j = 0; j < BP_RPT / 2; ++j) {
+                const float2 dr2 = __ffma2_rn(make_float2(ir[2 * j], ir[2 * j + 1]), make_float2(c4.y, c4.y), make_float2(c4.z, c4.z));
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float da = fmaf(jc[c], c4.x, dr0), db = KINK ? fmaf(jc[c], c5.x, dr0b) : 0.0f;
-                const float ds0 = !KINK ? da : (use_min ? fminf(da, db) : fmaxf(da, db));
-                if (2 * j + c < BpShare<V>::value) {
-                    shared_pair(pos_tag, ds0, c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
-                } else {
-                    single(ds0, c4, bw, seg, acc[2 * j][c]);
-                    single(dstar(jc[c], ir[2 * j + 1]), c4, bw, seg, acc[2 * j + 1][c]);
+                for (int c = 0; c < 2; ++c)
+                    pixel_pair(__ffma2_rn(make_float2(jc[c], jc[c]), make_float2(c4.x, c4.x), dr2), c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < BP_RPT / 2; ++j) {
+                const float dr0 = fmaf(ir[2 * j], c4.y, c4.z), dr0b = KINK ? fmaf(ir[2 * j], c5.y, c5.z) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float da = fmaf(jc[c], c4.x, dr0), db = KINK ? fmaf(jc[c], c5.x, dr0b) : 0.0f;
+                    const float ds0 = !KINK ? da : (use_min ? fminf(da, db) : fmaxf(da, db));
+                    if (2 * j + c < BpShare<V>::value) {
+                        shared_pair(pos_tag, ds0, c4, bw, seg, acc[2 * j][c], acc[2 * j + 1][c]);
+                    } else {
+                        single(ds0, c4, bw, seg, acc[2 * j][c]);
+                        single(dstar(jc[c], ir[2 * j + 1]), c4, bw, seg, acc[2 * j + 1][c]);
+                    }
                 }
             }
         }

@@ -217,6 +217,10 @@ __device__ __forceinline__ void tap_pair_fma(float w0, const float (&v0)[V], flo
         lo = __ffma2_rn(W0, make_float2(v0[0], v0[1]), __ffma2_rn(W1, make_float2(v1[0], v1[1]), lo));
         hi = __ffma2_rn(W0, make_float2(v0[2], v0[3]), __ffma2_rn(W1, make_float2(v1[2], v1[3]), hi));
         a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+    } else if constexpr (V == 2 && WT_FFMA2) {
+        float2 lo = make_float2(a[0], a[1]);
+        lo = __ffma2_rn(make_float2(w0, w0), make_float2(v0[0], v0[1]), __ffma2_rn(make_float2(w1, w1), make_float2(v1[0], v1[1]), lo));
+        a[0] = lo.x; a[1] = lo.y;
     } else {
 #pragma unroll
         for (int i = 0; i < V; ++i) a[i] = fmaf(w0, v0[i], fmaf(w1, v1[i], a[i]));

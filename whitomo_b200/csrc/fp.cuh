@@ -226,6 +226,46 @@ __device__ __forceinline__ float warp_ginv_f(const float (*wg)[FP_AT], const flo
     return copysignf(fmaf(a - wg[si][k], wi[si][k], pos), z);
 }
 
+// Two consecutive lines of one ray at once -- the float and float2 kernels (one or two images per position), which are
+// bound by the instruction issue rate, not by shared-memory wavefronts (11-13 issue slots per line for 1-2 updates).  The
+// index arithmetic of the two lines goes through the packed fp32 pipe of sm_100 (FADD2 / FFMA2: one issue slot, each half
+// rounded like the scalar operation; x - y is written fma(y, -1, x), whose product is exact), so positions, weights and
+// the order of the sum keep their bits: 8 slots per line.  (In the float4 kernel, which is wavefront-bound, the same
+// packing measured slower.)  `cr`: c - 1/2 relative to the window start on the two lines; `row`: the first line's window
+// minus MAGIC_BITS elements (indexed with the raw bits of the rounded sums: one address instruction per line).
+#ifndef WT_FP_PAIRLINES
+#define WT_FP_PAIRLINES 1
+#endif
+template <int V>
+__device__ __forceinline__ void fp_line_pair(float2 cr, const typename VecOf<V>::T *row, float (&acc)[V], float &acc_odd) {
+    constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
+    constexpr int MAGIC_BITS = 0x4B400000;
+    const float2 t = __fadd2_rn(cr, make_float2(MAGIC, MAGIC));
+    const float2 u = __fadd2_rn(t, make_float2(-MAGIC, -MAGIC));
+    const float2 r = __ffma2_rn(u, make_float2(-1.0f, -1.0f), cr);
+    const float2 off = __fadd2_rn(r, make_float2(0.5f, 0.5f));
+    const float2 w0 = __ffma2_rn(off, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+    check_index(__float_as_int(t.x) - MAGIC_BITS, __float_as_int(t.x) - MAGIC_BITS + 1, FP_W);
+    check_index(__float_as_int(t.y) - MAGIC_BITS, __float_as_int(t.y) - MAGIC_BITS + 1, FP_W);
+    const typename VecOf<V>::T *ta = row + __float_as_int(t.x), *tb = (row + FP_W) + __float_as_int(t.y);
+    float a0[V], a1[V], b0[V], b1[V];
+    unpack<V>(ta[0], a0);
+    unpack<V>(ta[1], a1);
+    unpack<V>(tb[0], b0);
+    unpack<V>(tb[1], b1);
+    if constexpr (V == 1) {
+        // one image: the FMAs of the two lines are packed too, the second line of every pair summing into `acc_odd`
+        // (added to the ray sum after the last chunk)
+        float2 s2 = make_float2(acc[0], acc_odd);
+        s2 = __ffma2_rn(off, make_float2(a1[0], b1[0]), __ffma2_rn(w0, make_float2(a0[0], b0[0]), s2));
+        acc[0] = s2.x;
+        acc_odd = s2.y;
+    } else {
+        tap_pair_fma<V>(off.x, a1, w0.x, a0, acc);
+        tap_pair_fma<V>(off.y, b1, w0.y, b0, acc);
+    }
+}
+
 // Epilogue contract: epi.operator()<W>(p, g, a, d, valid, val[W], cta_scratch, pass, npass) handles the W images of
 // group g (image index g*W + i) for ray (a, d); it is called by ALL threads of the CTA (it may synchronise).  Under
 // MIRROR the V components are V/2 images x {ray (a, d), mirrored ray (a, D-1-d)}: the epilogue then runs twice with
@@ -399,7 +439,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         }
     };
 
-    float acc[V];
+    float acc[V], acc_odd = 0.0f;   // (acc_odd: fp_line_pair<1>)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.0f;
     constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer
@@ -432,8 +472,20 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
                 // values a few positions apart is exact
                 const float wsh = sm.wstart[s] + 0.5f;
                 const VecT *row = &sm.seg[s][la - l0][0];
+                int l = la;
+                if constexpr (V <= 2 && WT_FP_PAIRLINES) {
+                    const VecT *rowb = row - MAGIC_BITS;
 #pragma unroll 4
-                for (int l = la; l < lb; ++l) {
+                    for (; l + 1 < lb; l += 2) {
+                        const float ca = c_run, cb = ca + delta;
+                        c_run = cb + delta;
+                        fp_line_pair<V>(__fadd2_rn(make_float2(ca, cb), make_float2(-wsh, -wsh)), rowb, acc, acc_odd);
+                        rowb += 2 * FP_W;
+                    }
+                    row = rowb + MAGIC_BITS;
+                }
+#pragma unroll 4
+                for (; l < lb; ++l) {
                     const float cr = c_run - wsh;
                     const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
                     const float off = (cr - (t - MAGIC)) + 0.5f;
@@ -461,8 +513,20 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
                 // c - 0.5 relative to the window start at line la; then one FADD per line
                 float cr = fmaf((float)la, delta, c0h) - sm.wstart[s];
                 const VecT *row = &sm.seg[s][la - l0][0];
+                int l = la;
+                if constexpr (V <= 2 && WT_FP_PAIRLINES) {
+                    const VecT *rowb = row - MAGIC_BITS;
 #pragma unroll 4
-                for (int l = la; l < lb; ++l) {
+                    for (; l + 1 < lb; l += 2) {
+                        const float cb = cr + delta;
+                        fp_line_pair<V>(make_float2(cr, cb), rowb, acc, acc_odd);
+                        cr = cb + delta;
+                        rowb += 2 * FP_W;
+                    }
+                    row = rowb + MAGIC_BITS;
+                }
+#pragma unroll 4
+                for (; l < lb; ++l) {
                     const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
                     const float off = (cr - (t - MAGIC)) + 0.5f;
                     const int idx = __float_as_int(t) - MAGIC_BITS;
@@ -481,6 +545,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         }
     }
 
+    if constexpr (V == 1) acc[0] += acc_odd;
     WT_TRACE_POINT(0, 4, tid == 0);
     if (cs > 1) {
         // partial ray sums of ranks 1 .. cs-1 travel to rank 0's shared memory: part[rank - 1][component][thread]
