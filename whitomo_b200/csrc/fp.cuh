@@ -40,7 +40,17 @@ constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only driv
 #endif
 constexpr int FP_LB = WT_FP_LB;  // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
-constexpr int FP_STAGES = WT_FP_STAGES;
+constexpr int FP_STAGES = WT_FP_STAGES;   // float4 kernels (and the least any kernel has: epilogues size their scratch with it)
+// The float / float2 kernels get through a chunk 3-4 times faster than the float4 kernel, so a chunk's time no longer
+// covers the latency of the next tiled copy (ncu, 2048^2 x 1800, one image, two stages: 19 % of the warp samples sit on
+// the full-barrier wait); their stages are 6 / 12 KB, so a deeper pipeline costs no occupancy.
+#ifndef WT_FP_STAGES_V1
+#define WT_FP_STAGES_V1 4
+#endif
+#ifndef WT_FP_STAGES_V2
+#define WT_FP_STAGES_V2 3
+#endif
+template <int V> struct FpStages { static constexpr int value = V == 1 ? WT_FP_STAGES_V1 : V == 2 ? WT_FP_STAGES_V2 : FP_STAGES; };
 // budget of the window for the host-side tiling: spread of ray positions across the tile must leave room
 // for the rounding margin (2 left, 3 right) and the 16-byte alignment of the window start (<= 3 positions)
 // (the 9th position of the margin absorbs the residual of the warped closed form that places the windows)
@@ -197,10 +207,12 @@ struct FpEpiStore {
 template <int V>
 struct FpSmem {
     typedef typename VecOf<V>::T VecT;
-    VecT seg[FP_STAGES][FP_LB][FP_W];
-    uint64_t full[FP_STAGES];   // TMA bytes of a stage have landed
-    uint64_t empty[FP_STAGES];  // all consumer warps are done reading a stage
-    float wstart[FP_STAGES];
+    static constexpr int NS = FpStages<V>::value;
+    static_assert(NS >= FP_STAGES, "epilogues count on FP_STAGES stages of scratch");
+    VecT seg[NS][FP_LB][FP_W];
+    uint64_t full[NS];   // TMA bytes of a stage have landed
+    uint64_t empty[NS];  // all consumer warps are done reading a stage
+    float wstart[NS];
     float zmin[FP_AT], delta[FP_AT];   // per angle of the tile: left-most ray at line 0 in unwarped coordinates, slope
     // the angles' position warps, entry-major: the producer's 8 lanes (one per angle) read 8 consecutive words
     float wg[16][FP_AT], wi[16][FP_AT];
@@ -277,6 +289,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FpSmem<V> &sm = *reinterpret_cast<FpSmem<V> *>(smem_raw);
 
+    constexpr int NS = FpStages<V>::value;   // pipeline depth
+    constexpr int TAIL_UNROLL = (V <= 2 && WT_FP_PAIRLINES) ? 1 : 4;   // line-by-line loop: all lines (float4), or the odd line left over
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp = 16 detectors x 2 angles; quarter-warp = 4 detectors x 2 angles
     const int slot = (warp >> 1) * 2 + (lane & 1);
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
     WT_TRACE_POINT(0, 1, tid == 0);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < FP_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], FP_THREADS / 32);
         }
@@ -414,7 +428,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         return (ws + VPAD) & ~(4 / V - 1);          // slot index (>= 0), 16-byte aligned
     };
     auto issue = [&](int ch, int ws) {
-        const int s = ch % FP_STAGES;
+        const int s = ch % NS;
         const int l0 = Lb + (ch0 + ch) * FP_LB;
         const int nl = min(l0 + FP_LB, nlines) - l0;
         if (lane == 0) {
@@ -446,11 +460,11 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
     constexpr int MAGIC_BITS = 0x4B400000;
 
     if (producer) {
-        // runs ahead of the consumers by up to FP_STAGES chunks; a stage is refilled as soon as all 8 consumer
+        // runs ahead of the consumers by up to NS chunks; a stage is refilled as soon as all 8 consumer
         // warps have released it -- consumer warps never wait for each other, only for data
         for (int ch = 0; ch < nchunk; ++ch) {
             const int ws = plan(ch);
-            if (ch >= FP_STAGES) mbar_wait(&sm.empty[ch % FP_STAGES], (uint32_t)(((ch / FP_STAGES) - 1) & 1));
+            if (ch >= NS) mbar_wait(&sm.empty[ch % NS], (uint32_t)(((ch / NS) - 1) & 1));
             issue(ch, ws);
         }
     } else if (!MIRROR && p.astra) {
@@ -462,8 +476,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
             for (int l = 0; l < lskip; ++l) c_run += delta;
         }
         for (int ch = 0; ch < nchunk; ++ch) {
-            const int s = ch % FP_STAGES;
-            mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
+            const int s = ch % NS;
+            mbar_wait(&sm.full[s], (uint32_t)((ch / NS) & 1));
             WT_TRACE_POINT(0, 3, tid == 0 && ch == 0);
             const int l0 = Lb + (ch0 + ch) * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
@@ -475,6 +489,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
                 int l = la;
                 if constexpr (V <= 2 && WT_FP_PAIRLINES) {
                     const VecT *rowb = row - MAGIC_BITS;
+                    // (a separate, fully unrolled path for whole chunks -- no loop control, constant offsets -- measured
+                    // slower from 1024^2 on: 3.83 vs 3.65 ms at 2048^2 x 1800, one image)
 #pragma unroll 4
                     for (; l + 1 < lb; l += 2) {
                         const float ca = c_run, cb = ca + delta;
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
                     }
                     row = rowb + MAGIC_BITS;
                 }
-#pragma unroll 4
+#pragma unroll(TAIL_UNROLL)
                 for (; l < lb; ++l) {
                     const float cr = c_run - wsh;
                     const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
@@ -505,8 +521,8 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
         }
     } else {
         for (int ch = 0; ch < nchunk; ++ch) {
-            const int s = ch % FP_STAGES;
-            mbar_wait(&sm.full[s], (uint32_t)((ch / FP_STAGES) & 1));
+            const int s = ch % NS;
+            mbar_wait(&sm.full[s], (uint32_t)((ch / NS) & 1));
             const int l0 = Lb + (ch0 + ch) * FP_LB;
             const int la = max(l0, l_lo), lb = min(l0 + FP_LB, l_hi);
             if (la < lb) {
@@ -525,7 +541,7 @@ __global__ void __launch_bounds__(FP_BLOCK) fp_kernel(FpParams p, Epi epi, const
                     }
                     row = rowb + MAGIC_BITS;
                 }
-#pragma unroll 4
+#pragma unroll(TAIL_UNROLL)
                 for (; l < lb; ++l) {
                     const float t = cr + MAGIC;             // round(c - 0.5) = floor(c) (ties: either neighbour, same value)
                     const float off = (cr - (t - MAGIC)) + 0.5f;
