@@ -256,8 +256,19 @@ constexpr int BP_MAX_SUMS = 4;
 
 // Epilogue contract: epi.operator()<W>(p, g, row, col, val[W]) handles the W images of group g for one pixel.  Under
 // MIRROR the V components are V/2 images x {pixel (row, col), its point reflection (R-1-row, C-1-col)}.
+// Resident CTAs per SM: three for the float4 kernels (72 registers: 32 accumulators + 12 live taps).  Measured for the
+// float / float2 kernels (BP at 2048^2 x 1800 / 512^2 x 360, ms): one image 3 / 4 / 5 / 6 CTAs: 3.39 / 3.41 / 3.64 (spills) /
+// 4.26; two images 3 / 4 CTAs: 4.00 / 3.99 and 0.082 / 0.079.
+#ifndef WT_BP_MINCTAS_V1
+#define WT_BP_MINCTAS_V1 3
+#endif
+#ifndef WT_BP_MINCTAS_V2
+#define WT_BP_MINCTAS_V2 4
+#endif
+template <int V> struct BpMinCtas { static constexpr int value = V == 1 ? WT_BP_MINCTAS_V1 : V == 2 ? WT_BP_MINCTAS_V2 : 3; };
+
 template <int V, class Epi, bool MIRROR, int TH>
-__global__ void __launch_bounds__(BP_BLOCK, 3) bp_kernel(BpParams p, Epi epi) {
+__global__ void __launch_bounds__(BP_BLOCK, BpMinCtas<V>::value) bp_kernel(BpParams p, Epi epi) {
     typedef typename VecOf<V>::T VecT;
     constexpr int BP_TH = TH, BP_RPT = BpTile<TH>::RPT, BP_SEGW = BpTile<TH>::SEGW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
