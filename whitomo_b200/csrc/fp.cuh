@@ -41,9 +41,9 @@ constexpr int FP_BLOCK = FP_THREADS + 32;  // + one producer warp that only driv
 constexpr int FP_LB = WT_FP_LB;  // lines per staged chunk
 constexpr int FP_W = 96;        // positions per staged line window
 constexpr int FP_STAGES = WT_FP_STAGES;   // float4 kernels (and the least any kernel has: epilogues size their scratch with it)
-// The float / float2 kernels get through a chunk 3-4 times faster than the float4 kernel, so a chunk's time no longer
-// covers the latency of the next tiled copy (ncu, 2048^2 x 1800, one image, two stages: 19 % of the warp samples sit on
-// the full-barrier wait); their stages are 6 / 12 KB, so a deeper pipeline costs no occupancy.
+// The float / float2 kernels get through a chunk 3-4 times faster than the float4 kernel and their stages are 6 / 12 KB,
+// so a deeper pipeline costs no occupancy: measured at 2048^2 x 1800, 2 / 3 / 4 / 6 / 8 stages: one image 3.71 / 3.66 /
+// 3.65 / 3.62 / 3.62 ms, two images 4.31 / 4.16 / - / 4.23 / 4.23 ms (512^2, two images: 8 stages cost occupancy, 0.111 vs 0.086).
 #ifndef WT_FP_STAGES_V1
 #define WT_FP_STAGES_V1 4
 #endif
