@@ -207,6 +207,13 @@ int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, 
                       const wt_update_params *prm, const unsigned char *active, double *penalty, void *ws,
                       size_t ws_bytes, void *stream);
 
+/* sum_i (c0_i c1_i)^2 of every slice, as WT_PAIR_NORM_BLOCKS float64 partial sums per slice in a fixed summation order
+ * (the caller adds them, e.g. once after its loop): the dissimilarity term ||beta c0 c1|| of the loss the reference's
+ * Iteration reports every step (src/white_rec.py:236-237: np.linalg.norm(beta_reg * c[0] * c[1])) -- one launch, no
+ * temporaries, no host sync.  conc: (nslices, 2, npix); out: (nslices, WT_PAIR_NORM_BLOCKS) float64. */
+#define WT_PAIR_NORM_BLOCKS 32
+int wt_pair_norm2(const float *conc, int nslices, size_t npix, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

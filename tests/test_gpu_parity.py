@@ -215,6 +215,22 @@ def test_white_fp_stack_and_odd_k(eng, golden):
             assert abs(loss[s].item() - 0.5 * np.sum(q ** 2)) < 1e-4 * 0.5 * np.sum(q ** 2)
 
 
+def test_pair_norm2_vs_numpy(eng):
+    """wt_pair_norm2: ||c0 c1|| of the loss Iteration reports (src/white_rec.py:236-237), ragged pixel counts included"""
+    Projector, _ = eng
+    rng = np.random.default_rng(21)
+    for S, r, c in ((1, 32, 32), (3, 70, 90), (2, 257, 129)):
+        P = Projector(r, c, int(np.hypot(r, c)) + 2, np.linspace(0, np.pi, 4))
+        x = rng.uniform(0.0, 1.0, (S, 2, r, c)).astype(np.float32)
+        part = P.pair_norm2(torch.from_numpy(x).cuda())
+        assert part.shape == (S, 32) and part.dtype == torch.float64
+        got = torch.sqrt(part.sum(-1)).cpu().numpy()
+        ref = [np.linalg.norm((x[s, 0] * x[s, 1]).astype(np.float64)) for s in range(S)]
+        assert np.allclose(got, ref, rtol=1e-6)
+        again = P.pair_norm2(torch.from_numpy(x).cuda())
+        assert torch.equal(part, again)          # fixed summation order
+
+
 def test_barrier_update_vs_numpy(eng):
     Projector, _ = eng
     P = Projector(32, 32, 46, np.linspace(0, np.pi, 8))

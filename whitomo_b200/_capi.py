@@ -42,7 +42,9 @@ SIGNATURES = {
     "wt_step_times": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
     "wt_barrier_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "wt_pair_norm2": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
 }
+PAIR_NORM_BLOCKS = 32      # WT_PAIR_NORM_BLOCKS of include/whitomo_b200.h
 
 
 

@@ -925,3 +925,35 @@ int wt_barrier_update(float *x, const float *grad, int nslices, int n_elements, 
 }
 
 }  // extern "C"
+
+// ---- ||c0 c1||^2 per slice (the loss term of src/white_rec.py:236-237) ------------------------------------------------
+// grid (WT_PAIR_NORM_BLOCKS, nslices): block b reduces a contiguous slab of the slice in float64 (the product itself is a
+// float32 product, like the reference's array arithmetic on float32 data), fixed order within the block.
+__global__ void __launch_bounds__(256) pair_norm2_kernel(const float *__restrict__ c, size_t npix, double *__restrict__ out) {
+    const float *c0 = c + (size_t)blockIdx.y * 2 * npix, *c1 = c0 + npix;
+    const size_t per = (npix + gridDim.x - 1) / gridDim.x;
+    const size_t i0 = (size_t)blockIdx.x * per, i1 = i0 + per < npix ? i0 + per : npix;
+    double acc = 0.0;
+    for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float pr = __fmul_rn(__ldg(c0 + i), __ldg(c1 + i));
+        acc += (double)pr * (double)pr;
+    }
+    acc = wt::warp_sum(acc);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+int wt_pair_norm2(const float *conc, int nslices, size_t npix, double *out, void *stream) {
+    if (!conc || !out) return invalid("wt_pair_norm2: null pointer");
+    if (nslices <= 0 || npix == 0) return invalid("wt_pair_norm2: bad sizes");
+    pair_norm2_kernel<<<dim3(WT_PAIR_NORM_BLOCKS, nslices), 256, 0, (cudaStream_t)stream>>>(conc, npix, out);
+    WT_CUDA(cudaGetLastError());
+    return WT_OK;
+}
+

@@ -332,6 +332,20 @@ class Projector(object):
         return u, pr, st
 
     @_on_own_device
+    def pair_norm2(self, conc, out=None):
+        """Partial sums of sum_i (c0_i c1_i)^2 per slice (wt_pair_norm2): conc (S, 2, rows, cols) float32 ->
+        (S, PAIR_NORM_BLOCKS) float64; ``.sum(-1).sqrt()`` is the ||c0 c1|| of src/white_rec.py:236-237.  ``out``: where
+        to write them (a solver loop passes a row of its history buffer: one launch per iteration, nothing else)."""
+        if conc.dtype != torch.float32 or not conc.is_contiguous() or conc.device != self.device or conc.dim() != 4 or conc.shape[1] != 2:
+            raise ValueError("conc must be a contiguous float32 (S, 2, rows, cols) tensor on %s" % self.device)
+        S = conc.shape[0]
+        if out is None:
+            out = torch.empty((S, _capi.PAIR_NORM_BLOCKS), dtype=torch.float64, device=self.device)
+        elif out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != S * _capi.PAIR_NORM_BLOCKS or out.device != self.device:
+            raise ValueError("out must be a contiguous float64 tensor of S x %d values" % _capi.PAIR_NORM_BLOCKS)
+        _capi.check(self.lib.wt_pair_norm2(_ptr(conc), S, conc.shape[-1] * conc.shape[-2], _ptr(out), _stream()))
+        return out
+
     def barrier_update(self, x, grad, alpha, beta_reg, t, reg_w=0.0, triv_w=0.0, lower_only=False,
                        mode=_capi.UPD_STEP_CLIP, elem_mask=0xFFFFFFFF, active=None, want_penalty=False):
         """In-place fused K3 step (wt_barrier_update).  x, grad: (S, K, rows, cols) / (K, rows, cols) / (rows, cols)."""

@@ -199,13 +199,20 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
     if fused:       # three launches per iteration (K2 + step, K1, reduction), see white_barrier_stack
         state = proj.new_step_state(spectrum, S)
         f_loss, _ = proj.white_barrier_step(spectrum, c, meas, state, init=True)
-    f_hist, r_hist = [], []             # per iteration: f (S,) float64 and ||c0 c1|| (S,); combined after the loop
+    f_hist = []                         # per iteration: f (S,) float64; combined with ||c0 c1|| after the loop
+    want_r = dissimilarity_constraint and K == 2
+    pair_norm2 = getattr(proj, "pair_norm2", None)        # (the numpy drop-in of the tests has none)
+    r_part = torch.empty((n_iters, S, _capi.PAIR_NORM_BLOCKS), dtype=torch.float64, device=c.device) \
+        if (want_r and pair_norm2 is not None and n_iters > 0) else None
+    r_hist = []
     for it in range(start_iter, start_iter + n_iters):
         if not fused:
             _, qmu, f_loss = proj.white_fp(spectrum, c, meas=meas, want_intensity=False)
             g = proj.bp(qmu.reshape((S * K,) + proj.sino_shape), scale=-1.0)
         f_hist.append(f_loss)
-        if dissimilarity_constraint and K == 2:
+        if r_part is not None:          # sum (c0 c1)^2 as partial sums: one launch, reduced after the loop
+            pair_norm2(c, out=r_part[it - start_iter])
+        elif want_r:
             r_hist.append(torch.linalg.vector_norm((c[:, 0] * c[:, 1]).reshape(S, -1), dim=1))
         mask = 0xFFFFFFFF
         if alternate and K == 2:
@@ -215,10 +222,12 @@ def white_rec_stack(proj, spectrum, meas, c0, n_iters=1000, alpha=0.7, beta_reg=
                                                 triv_w=triv_w, mode=mode, elem_mask=mask)
         else:
             proj.barrier_update(c, g, alpha, beta_reg, 0.0, reg_w=reg_w, triv_w=triv_w, mode=mode, elem_mask=mask)
-    # losses[i] = ||q_i|| + ||beta c0 c1||: two small kernels per iteration inside the loop, the rest once here
+    # losses[i] = ||q_i|| + ||beta c0 c1||: one small kernel per iteration inside the loop, the rest once here
     if f_hist:
         total = torch.sqrt(2.0 * torch.stack(f_hist))
-        if r_hist:
+        if r_part is not None:
+            total = total + abs(beta_reg) * torch.sqrt(r_part.sum(-1))
+        elif r_hist:
             total = total + abs(beta_reg) * torch.stack(r_hist).double()
         losses = list(total.unbind(0))
     return c, losses
