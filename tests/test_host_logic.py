@@ -231,6 +231,19 @@ def test_plan_rejects_bad_geometries_without_cuda():
     assert lib.wt_geom_plan(8, 8, 8, 1.0, fp, 4, 0, none, none, none, none, ctypes.byref(nt), none, none) == 0 and nt.value >= 1
 
 
+def test_data_calls_reject_bad_arguments_before_touching_cuda():
+    """argument checks of the data entry points come first: no GPU needed to see WT_ERR_INVALID (-1)"""
+    from whitomo_b200 import _capi
+    lib = _capi.load()
+    assert lib.wt_pair_norm2(None, 1, 16, None, None) == -1 and b"wt_pair_norm2" in lib.wt_last_error()
+    buf = (ctypes.c_double * 32)()
+    x = (ctypes.c_float * 32)()
+    assert lib.wt_pair_norm2(ctypes.addressof(x), 0, 16, ctypes.addressof(buf), None) == -1
+    assert lib.wt_pair_norm2(ctypes.addressof(x), 1, 0, ctypes.addressof(buf), None) == -1
+    assert lib.wt_fp(None, None, None, 1, 0, 1, None, 0, None) == -1 and b"wt_fp" in lib.wt_last_error()
+    assert lib.wt_barrier_update(None, None, 1, 1, 16, None, None, None, None, 0, None) == -1
+
+
 @pytest.mark.parametrize("n,na,ndblk", [(64, 48, 3), (256, 180, 12), (2048, 1800, 91)])
 def test_launch_order_visits_every_cta_once(n, na, ndblk):
     """fp.cuh: fp_block maps the linear block index to (tile, detector block): phase by phase, detector blocks slowest
